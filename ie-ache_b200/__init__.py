@@ -1,0 +1,258 @@
+"""ieache_b200 — ctypes binding of libieache_b200.so, the B200-native TFHE gate-bootstrapping engine
+that replaces libtfhe under IE-ACHE's Cloud node (Cloud/cloud.c).
+
+This is the host-side mirror of the reference's interface for the hot path:
+
+* ``Engine.gate_batch``    — `count` independent ``boots<OP>`` calls (Cloud/cloud.c:30-43) in one launch
+* ``Engine.circuit``/``eval`` — the add / subtract / multiply circuits of Cloud/cloud.c:18-647, levelised
+* ``Engine.cloud_run``     — the ``subprocess.call("./cloud")`` contract of
+  Cloud/dragonfly_cipher_cloud.py:1233 (reads cloud.key, nbit.key, cloud.data, operator.txt; writes answer.data)
+
+There is no CPU fallback: importing works anywhere (so the symbol table can be checked on a CPU
+box), but every compute call needs the CUDA library and a B200 and raises ``EngineError`` otherwise.
+The directory name carries a hyphen (``ie-ache_b200``); load it with ``__graft_entry__.load_package()``
+or put the repo root on ``sys.path`` and use ``importlib`` — it registers itself as ``ieache_b200``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_int32, c_size_t, c_uint32, c_uint64, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libieache_b200.so")
+
+DEVICE_STRIDE = 632
+
+OPS = {
+    "NAND": 0, "OR": 1, "AND": 2, "XOR": 3, "XNOR": 4, "NOR": 5, "ANDNY": 6, "ANDYN": 7,
+    "ORNY": 8, "ORYN": 9, "MUX": 10, "NOT": 11, "COPY": 12, "CONST": 13,
+}
+CIRC_ADD, CIRC_SUB, CIRC_MUL, CIRC_MULADD = 1, 2, 4, 5
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class Params(ctypes.Structure):
+    _fields_ = [(k, c_int32) for k in ("n", "N", "k", "bk_l", "bk_Bgbit", "ks_t", "ks_basebit", "reserved")] + [
+        (k, c_double) for k in ("ks_stdev", "bk_stdev", "max_stdev")
+    ]
+
+    @classmethod
+    def default(cls, n: int = 630) -> "Params":
+        """new_default_gate_bootstrapping_parameters(110) (Keygen/keygen.c:22-23) with n overridable for tests."""
+        return cls(n, 1024, 1, 3, 7, 8, 2, 0, 2.0 ** -15, 2.0 ** -25, 0.012467)
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load the CUDA extension; fail loudly if it is missing (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback."
+        )
+    L = ctypes.CDLL(LIB_PATH)
+    L.ieache_last_error.restype = c_char_p
+    L.ieache_version.restype = c_char_p
+    L.ieache_ctx_launch_count.restype = c_uint64
+    L.ieache_ctx_launch_count.argtypes = [c_void_p]
+    L.ieache_ctx_create.argtypes = [c_int, POINTER(c_void_p)]
+    L.ieache_ctx_destroy.argtypes = [c_void_p]
+    L.ieache_ctx_sync.argtypes = [c_void_p]
+    L.ieache_ctx_set_timing.argtypes = [c_void_p, c_int]
+    L.ieache_ctx_kernel_times.argtypes = [c_void_p, POINTER(c_double), POINTER(c_double), POINTER(c_uint64), POINTER(c_uint64), c_int]
+    L.ieache_cloudkey_create.argtypes = [c_void_p, POINTER(Params), c_void_p, c_void_p, POINTER(c_void_p)]
+    L.ieache_cloudkey_load_file.argtypes = [c_void_p, c_char_p, POINTER(c_void_p)]
+    L.ieache_cloudkey_destroy.argtypes = [c_void_p]
+    L.ieache_cloudkey_params.argtypes = [c_void_p, POINTER(Params)]
+    L.ieache_cloudkey_device_arrays.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_size_t), POINTER(c_void_p), POINTER(c_size_t)]
+    L.ieache_cloudkey_device_sizes.argtypes = [POINTER(Params), POINTER(c_size_t), POINTER(c_size_t)]
+    L.ieache_cloudkey_adopt_device.argtypes = [c_void_p, POINTER(Params), c_void_p, c_void_p, POINTER(c_void_p)]
+    L.ieache_gate_batch.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_size_t]
+    L.ieache_gate_batch_device.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_size_t]
+    L.ieache_bootstrap_woks.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]
+    L.ieache_keyswitch.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]
+    L.ieache_device_alloc.argtypes = [c_void_p, c_size_t, POINTER(c_void_p)]
+    L.ieache_device_free.argtypes = [c_void_p, c_void_p]
+    L.ieache_samples_to_device.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_int32]
+    L.ieache_samples_to_host.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_int32]
+    L.ieache_circuit_build.argtypes = [c_int, c_int, POINTER(c_void_p)]
+    L.ieache_circuit_destroy.argtypes = [c_void_p]
+    L.ieache_circuit_stats.argtypes = [c_void_p, POINTER(c_uint64), POINTER(c_uint64), POINTER(c_uint64), POINTER(c_uint32),
+                                       POINTER(c_uint32), POINTER(c_uint32), POINTER(c_uint32)]
+    L.ieache_circuit_eval.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]
+    L.ieache_circuit_eval_device.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]
+    L.ieache_cloud_run.argtypes = [c_void_p, c_char_p, POINTER(c_double)]
+    _lib = L
+    return L
+
+
+def _check(rc: int) -> None:
+    if rc < 0:
+        raise EngineError(f"ieache_b200 error {rc}: {lib().ieache_last_error().decode()}")
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data_as(c_void_p)
+    return c_void_p(int(a))  # raw device/host address
+
+
+class Circuit:
+    """Levelised DAG of one Cloud/cloud.c dispatch branch (kind x width)."""
+
+    def __init__(self, kind: int, width: int):
+        self._h = c_void_p()
+        _check(lib().ieache_circuit_build(kind, width, byref(self._h)))
+        b, a, x = c_uint64(), c_uint64(), c_uint64()
+        lv, mw, ni, no = c_uint32(), c_uint32(), c_uint32(), c_uint32()
+        _check(lib().ieache_circuit_stats(self._h, byref(b), byref(a), byref(x), byref(lv), byref(mw), byref(ni), byref(no)))
+        self.kind, self.width = kind, width
+        self.bootstraps, self.and_gates, self.xor_gates = b.value, a.value, x.value
+        self.levels, self.max_width, self.n_inputs, self.n_outputs = lv.value, mw.value, ni.value, no.value
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.ieache_circuit_destroy(self._h)
+            self._h = None
+
+
+class CloudKey:
+    def __init__(self, engine: "Engine", handle: c_void_p):
+        self.engine, self._h = engine, handle
+        p = Params()
+        _check(lib().ieache_cloudkey_params(handle, byref(p)))
+        self.params = p
+
+    def device_arrays(self):
+        bk, bkb, ks, ksb = c_void_p(), c_size_t(), c_void_p(), c_size_t()
+        _check(lib().ieache_cloudkey_device_arrays(self._h, byref(bk), byref(bkb), byref(ks), byref(ksb)))
+        return bk.value, bkb.value, ks.value, ksb.value
+
+    def close(self):
+        if self._h:
+            lib().ieache_cloudkey_destroy(self._h)
+            self._h = None
+
+
+class Engine:
+    """One engine context per process and GPU."""
+
+    def __init__(self, device: int = 0):
+        self._h = c_void_p()
+        _check(lib().ieache_ctx_create(device, byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().ieache_ctx_destroy(self._h)
+            self._h = None
+
+    # ---- keys -------------------------------------------------------------------------------
+    def cloud_key_from_arrays(self, params: Params, bk: np.ndarray, ksk: np.ndarray) -> CloudKey:
+        h = c_void_p()
+        _check(lib().ieache_cloudkey_create(self._h, byref(params), _ptr(bk), _ptr(ksk), byref(h)))
+        return CloudKey(self, h)
+
+    def cloud_key_from_file(self, path: str) -> CloudKey:
+        h = c_void_p()
+        _check(lib().ieache_cloudkey_load_file(self._h, path.encode(), byref(h)))
+        return CloudKey(self, h)
+
+    def cloud_key_adopt(self, params: Params, bkfft_dev: int, ksk_dev: int) -> CloudKey:
+        h = c_void_p()
+        _check(lib().ieache_cloudkey_adopt_device(self._h, byref(params), c_void_p(bkfft_dev), c_void_p(ksk_dev), byref(h)))
+        return CloudKey(self, h)
+
+    # ---- gates ------------------------------------------------------------------------------
+    def gate_batch(self, key: CloudKey, op, a=None, b=None, c=None, imm: int = 0, count: int | None = None) -> np.ndarray:
+        """`count` independent gates on host arrays of shape (count, n+1) int32."""
+        opc = OPS[op] if isinstance(op, str) else int(op)
+        n = key.params.n
+        if count is None:
+            count = len(a)
+        out = np.empty((count, n + 1), dtype=np.int32)
+        _check(lib().ieache_gate_batch(self._h, key._h, opc, _ptr(out), _ptr(a), _ptr(b), _ptr(c), imm, count))
+        return out
+
+    def gate_batch_device(self, key: CloudKey, op, out_dev: int, a_dev: int, b_dev: int = 0, c_dev: int = 0, imm: int = 0, count: int = 0):
+        opc = OPS[op] if isinstance(op, str) else int(op)
+        _check(lib().ieache_gate_batch_device(self._h, key._h, opc, c_void_p(out_dev), c_void_p(a_dev),
+                                              c_void_p(b_dev) if b_dev else None, c_void_p(c_dev) if c_dev else None, imm, count))
+
+    def bootstrap_woks(self, key: CloudKey, x: np.ndarray) -> np.ndarray:
+        out = np.empty((len(x), 1025), dtype=np.int32)
+        _check(lib().ieache_bootstrap_woks(self._h, key._h, _ptr(out), _ptr(x), len(x)))
+        return out
+
+    def keyswitch(self, key: CloudKey, ext: np.ndarray) -> np.ndarray:
+        out = np.empty((len(ext), key.params.n + 1), dtype=np.int32)
+        _check(lib().ieache_keyswitch(self._h, key._h, _ptr(out), _ptr(ext), len(ext)))
+        return out
+
+    # ---- device memory ----------------------------------------------------------------------
+    def device_alloc(self, nbytes: int) -> int:
+        p = c_void_p()
+        _check(lib().ieache_device_alloc(self._h, nbytes, byref(p)))
+        return p.value
+
+    def device_free(self, ptr: int):
+        _check(lib().ieache_device_free(self._h, c_void_p(ptr)))
+
+    def samples_to_device(self, dev: int, host, count: int, n: int):
+        _check(lib().ieache_samples_to_device(self._h, c_void_p(dev), _ptr(host), count, n))
+
+    def samples_to_host(self, host, dev: int, count: int, n: int):
+        _check(lib().ieache_samples_to_host(self._h, _ptr(host), c_void_p(dev), count, n))
+
+    def sync(self):
+        _check(lib().ieache_ctx_sync(self._h))
+
+    # ---- circuits ---------------------------------------------------------------------------
+    def circuit(self, kind: int, width: int) -> Circuit:
+        return Circuit(kind, width)
+
+    def eval(self, key: CloudKey, circ: Circuit, inputs: np.ndarray) -> np.ndarray:
+        """inputs: (n_expr, n_inputs, n+1) int32 -> (n_expr, n_outputs, n+1)."""
+        n_expr = inputs.shape[0]
+        assert inputs.shape[1] == circ.n_inputs
+        out = np.empty((n_expr, circ.n_outputs, key.params.n + 1), dtype=np.int32)
+        _check(lib().ieache_circuit_eval(self._h, key._h, circ._h, _ptr(inputs), _ptr(out), n_expr))
+        return out
+
+    def eval_device(self, key: CloudKey, circ: Circuit, in_dev: int, out_dev: int, n_expr: int):
+        _check(lib().ieache_circuit_eval_device(self._h, key._h, circ._h, c_void_p(in_dev), c_void_p(out_dev), n_expr))
+
+    # ---- the ./cloud process contract ---------------------------------------------------------
+    def cloud_run(self, directory: str) -> tuple[int, float]:
+        """Cloud/dragonfly_cipher_cloud.py:1233 `subprocess.call("./cloud")` without the subprocess."""
+        secs = c_double()
+        rc = lib().ieache_cloud_run(self._h, directory.encode(), byref(secs))
+        _check(rc)
+        return rc, secs.value
+
+    # ---- measurement --------------------------------------------------------------------------
+    def set_timing(self, on: bool):
+        _check(lib().ieache_ctx_set_timing(self._h, int(on)))
+
+    def kernel_times(self, reset: bool = True):
+        br, ks, nbr, nks = c_double(), c_double(), c_uint64(), c_uint64()
+        _check(lib().ieache_ctx_kernel_times(self._h, byref(br), byref(ks), byref(nbr), byref(nks), int(reset)))
+        return {"blind_rotate_ms": br.value, "keyswitch_ms": ks.value, "blind_rotate_launches": nbr.value, "keyswitch_launches": nks.value}
+
+    @property
+    def launch_count(self) -> int:
+        return lib().ieache_ctx_launch_count(self._h)

@@ -1,0 +1,621 @@
+/*
+ * engine.cu — host side of the C ABI in include/ieache_b200.h: device key management, batched
+ * gates, the levelised circuit executor and the Cloud node's process contract.
+ *
+ * No CPU compute path exists here: every gate goes through launch_blind_rotate /
+ * launch_keyswitch.  Host code only parses files, moves bytes and handles the nbit metadata
+ * that Cloud/cloud.c itself handles on the host (cloud.c:709-855).
+ */
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/ieache_b200.h"
+#include "circuit.h"
+#include "kernels.h"
+#include "tfhe_io.h"
+
+using namespace ieache;
+
+static thread_local std::string g_err;
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) return fail(IEACHE_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+extern "C" const char *ieache_last_error(void) { return g_err.c_str(); }
+extern "C" const char *ieache_version(void) { return "ieache_b200 0.1 (sm_100a)"; }
+
+/* ------------------------------------------------------------------ context */
+struct TimedLaunch { cudaEvent_t a, b; int kind; };
+
+struct ieache_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    int32_t *d_ext = nullptr; size_t ext_cap = 0;      /* extracted samples scratch */
+    int32_t *d_stage[4] = {nullptr, nullptr, nullptr, nullptr}; size_t stage_cap[4] = {0, 0, 0, 0};
+    int32_t *d_wires = nullptr; size_t wires_cap = 0;
+    bool timing = false;
+    std::vector<TimedLaunch> timed;
+    double br_ms = 0, ks_ms = 0; uint64_t br_n = 0, ks_n = 0;
+};
+
+static int ensure(ieache_ctx *ctx, int32_t **buf, size_t *cap, size_t words)
+{
+    if (*cap >= words) return IEACHE_OK;
+    if (*buf) { cudaStreamSynchronize(ctx->stream); cudaFree(*buf); *buf = nullptr; *cap = 0; }
+    CU(cudaMalloc((void **)buf, words * sizeof(int32_t)));
+    *cap = words;
+    return IEACHE_OK;
+}
+
+extern "C" int ieache_ctx_create(int device, ieache_ctx **out)
+{
+    if (!out) return fail(IEACHE_ERR_ARG, "null out");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(IEACHE_ERR_ARG, "device %d out of range (%d visible)", device, ndev);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(IEACHE_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    std::unique_ptr<ieache_ctx> ctx(new ieache_ctx());
+    ctx->device = device;
+    CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CU(upload_twiddles());
+    *out = ctx.release();
+    return IEACHE_OK;
+}
+extern "C" void ieache_ctx_destroy(ieache_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &t : ctx->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    cudaFree(ctx->d_ext);
+    for (int i = 0; i < 4; i++) cudaFree(ctx->d_stage[i]);
+    cudaFree(ctx->d_wires);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+extern "C" int ieache_ctx_sync(ieache_ctx *ctx)
+{
+    if (!ctx) return fail(IEACHE_ERR_ARG, "null ctx");
+    CU(cudaStreamSynchronize(ctx->stream));
+    return IEACHE_OK;
+}
+extern "C" uint64_t ieache_ctx_launch_count(const ieache_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int ieache_ctx_set_timing(ieache_ctx *ctx, int enabled)
+{
+    if (!ctx) return fail(IEACHE_ERR_ARG, "null ctx");
+    ctx->timing = enabled != 0;
+    return IEACHE_OK;
+}
+static int drain_timed(ieache_ctx *ctx)
+{
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (auto &t : ctx->timed) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, t.a, t.b));
+        if (t.kind == 0) { ctx->br_ms += ms; ctx->br_n++; } else { ctx->ks_ms += ms; ctx->ks_n++; }
+        cudaEventDestroy(t.a); cudaEventDestroy(t.b);
+    }
+    ctx->timed.clear();
+    return IEACHE_OK;
+}
+extern "C" int ieache_ctx_kernel_times(ieache_ctx *ctx, double *br_ms, double *ks_ms, uint64_t *br_n, uint64_t *ks_n, int reset)
+{
+    if (!ctx) return fail(IEACHE_ERR_ARG, "null ctx");
+    int rc = drain_timed(ctx);
+    if (rc) return rc;
+    if (br_ms) *br_ms = ctx->br_ms;
+    if (ks_ms) *ks_ms = ctx->ks_ms;
+    if (br_n) *br_n = ctx->br_n;
+    if (ks_n) *ks_n = ctx->ks_n;
+    if (reset) { ctx->br_ms = ctx->ks_ms = 0; ctx->br_n = ctx->ks_n = 0; }
+    return IEACHE_OK;
+}
+
+/* ------------------------------------------------------------------ cloud key */
+struct ieache_cloudkey {
+    ieache_ctx *ctx = nullptr;
+    ieache_params p{};
+    DevParams dp{};
+    double2 *bkfft = nullptr; size_t bkfft_bytes = 0;
+    int32_t *ksk = nullptr; size_t ksk_bytes = 0;
+    bool owns = true;
+};
+
+static int check_params(const ieache_params *p)
+{
+    if (!p) return fail(IEACHE_ERR_ARG, "null params");
+    if (p->N != 1024 || p->k != 1) return fail(IEACHE_ERR_UNSUPPORTED, "kernels support N=1024,k=1 (got N=%d,k=%d)", p->N, p->k);
+    if (p->bk_l != 2 && p->bk_l != 3) return fail(IEACHE_ERR_UNSUPPORTED, "kernels support bk_l in {2,3} (got %d)", p->bk_l);
+    if (p->n < 1 || p->n > kLweStride - 1) return fail(IEACHE_ERR_UNSUPPORTED, "kernels support 1 <= n <= %d (got %d)", kLweStride - 1, p->n);
+    if (p->bk_Bgbit < 1 || p->bk_Bgbit * p->bk_l > 31) return fail(IEACHE_ERR_UNSUPPORTED, "unsupported Bgbit=%d", p->bk_Bgbit);
+    if (p->ks_t < 1 || p->ks_basebit < 1 || p->ks_basebit * p->ks_t > 31 || p->ks_t > 16) return fail(IEACHE_ERR_UNSUPPORTED, "unsupported key-switch parameters t=%d basebit=%d", p->ks_t, p->ks_basebit);
+    return IEACHE_OK;
+}
+static void fill_dev_params(const ieache_params &p, DevParams &dp)
+{
+    dp.n = p.n; dp.l = p.bk_l; dp.Bgbit = p.bk_Bgbit; dp.ks_t = p.ks_t; dp.ks_basebit = p.ks_basebit;
+    dp.mu = 1 << 29; /* modSwitchToTorus32(1, 8) */
+}
+extern "C" int ieache_cloudkey_device_sizes(const ieache_params *p, size_t *bkfft_bytes, size_t *ksk_bytes)
+{
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (bkfft_bytes) *bkfft_bytes = (size_t)p->n * 2 * p->bk_l * 2 * 512 * sizeof(double2);
+    if (ksk_bytes) *ksk_bytes = (size_t)p->N * p->ks_t * ((1u << p->ks_basebit) - 1) * kLweStride * sizeof(int32_t);
+    return IEACHE_OK;
+}
+
+extern "C" int ieache_cloudkey_create(ieache_ctx *ctx, const ieache_params *p, const int32_t *bk, const int32_t *ksk,
+                                      ieache_cloudkey **out)
+{
+    if (!ctx || !bk || !ksk || !out) return fail(IEACHE_ERR_ARG, "null argument");
+    int rc = check_params(p);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    std::unique_ptr<ieache_cloudkey> key(new ieache_cloudkey());
+    key->ctx = ctx; key->p = *p; fill_dev_params(*p, key->dp);
+    ieache_cloudkey_device_sizes(p, &key->bkfft_bytes, &key->ksk_bytes);
+    const int kpl = 2 * p->bk_l, base = 1 << p->ks_basebit;
+    const size_t bk_words = (size_t)p->n * kpl * 2 * 1024;
+    const size_t ksk_words = (size_t)1024 * p->ks_t * base * (p->n + 1);
+    int32_t *d_tmp = nullptr;
+    CU(cudaMalloc((void **)&key->bkfft, key->bkfft_bytes));
+    CU(cudaMalloc((void **)&key->ksk, key->ksk_bytes));
+    CU(cudaMalloc((void **)&d_tmp, std::max(bk_words, ksk_words) * sizeof(int32_t)));
+    /* bkFFT on the GPU (libtfhe builds it on the CPU at key load) */
+    CU(cudaMemcpyAsync(d_tmp, bk, bk_words * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(launch_bk_fft(d_tmp, key->bkfft, p->n * kpl * 2, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpyAsync(d_tmp, ksk, ksk_words * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(launch_pack_ksk(d_tmp, key->ksk, 1024, p->ks_t, base, p->n, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->launches += 2;
+    cudaFree(d_tmp);
+    *out = key.release();
+    return IEACHE_OK;
+}
+
+extern "C" int ieache_cloudkey_load_file(ieache_ctx *ctx, const char *path, ieache_cloudkey **out)
+{
+    if (!ctx || !path || !out) return fail(IEACHE_ERR_ARG, "null argument");
+    HostKeySet hk;
+    std::string msg;
+    int rc = read_keyset(path, hk, true, msg);
+    if (rc) return fail(rc, "%s", msg.c_str());
+    return ieache_cloudkey_create(ctx, &hk.p, hk.bk.data(), hk.ksk.data(), out);
+}
+extern "C" void ieache_cloudkey_destroy(ieache_cloudkey *key)
+{
+    if (!key) return;
+    if (key->owns) {
+        cudaSetDevice(key->ctx->device);
+        cudaStreamSynchronize(key->ctx->stream);
+        cudaFree(key->bkfft); cudaFree(key->ksk);
+    }
+    delete key;
+}
+extern "C" int ieache_cloudkey_params(const ieache_cloudkey *key, ieache_params *out)
+{
+    if (!key || !out) return fail(IEACHE_ERR_ARG, "null argument");
+    *out = key->p;
+    return IEACHE_OK;
+}
+extern "C" int ieache_cloudkey_device_arrays(const ieache_cloudkey *key, void **bkfft, size_t *bkfft_bytes, void **ksk, size_t *ksk_bytes)
+{
+    if (!key) return fail(IEACHE_ERR_ARG, "null key");
+    if (bkfft) *bkfft = key->bkfft;
+    if (bkfft_bytes) *bkfft_bytes = key->bkfft_bytes;
+    if (ksk) *ksk = key->ksk;
+    if (ksk_bytes) *ksk_bytes = key->ksk_bytes;
+    return IEACHE_OK;
+}
+extern "C" int ieache_cloudkey_adopt_device(ieache_ctx *ctx, const ieache_params *p, void *bkfft, void *ksk, ieache_cloudkey **out)
+{
+    if (!ctx || !bkfft || !ksk || !out) return fail(IEACHE_ERR_ARG, "null argument");
+    int rc = check_params(p);
+    if (rc) return rc;
+    ieache_cloudkey *key = new ieache_cloudkey();
+    key->ctx = ctx; key->p = *p; fill_dev_params(*p, key->dp);
+    ieache_cloudkey_device_sizes(p, &key->bkfft_bytes, &key->ksk_bytes);
+    key->bkfft = (double2 *)bkfft; key->ksk = (int32_t *)ksk; key->owns = false;
+    *out = key;
+    return IEACHE_OK;
+}
+
+/* ------------------------------------------------------------------ launches with optional timing */
+static int run_br(ieache_ctx *ctx, const ieache_cloudkey *key, const GateAddr &ga, const int32_t *A, const int32_t *B, int ext_base)
+{
+    TimedLaunch t{};
+    if (ctx->timing) { CU(cudaEventCreate(&t.a)); CU(cudaEventCreate(&t.b)); t.kind = 0; CU(cudaEventRecord(t.a, ctx->stream)); }
+    CU(launch_blind_rotate(key->dp, key->bkfft, ga, A, B, ctx->d_ext, ext_base, ctx->stream));
+    if (ctx->timing) { CU(cudaEventRecord(t.b, ctx->stream)); ctx->timed.push_back(t); }
+    ctx->launches++;
+    return IEACHE_OK;
+}
+static int run_ks(ieache_ctx *ctx, const ieache_cloudkey *key, const GateAddr &ga, int32_t *out, int pair_offset, int32_t cst_post)
+{
+    TimedLaunch t{};
+    if (ctx->timing) { CU(cudaEventCreate(&t.a)); CU(cudaEventCreate(&t.b)); t.kind = 1; CU(cudaEventRecord(t.a, ctx->stream)); }
+    CU(launch_keyswitch(key->dp, key->ksk, ga, out, ctx->d_ext, pair_offset, cst_post, ctx->stream));
+    if (ctx->timing) { CU(cudaEventRecord(t.b, ctx->stream)); ctx->timed.push_back(t); }
+    ctx->launches++;
+    if (ctx->timed.size() > 4096) return drain_timed(ctx);
+    return IEACHE_OK;
+}
+
+/* ------------------------------------------------------------------ batched gates */
+static const int8_t k_lin[10][3] = {{+1, -1, -1}, {+1, +1, +1}, {-1, +1, +1}, {+2, +2, +2}, {-2, -2, -2},
+                                    {-1, -1, -1}, {-1, -1, +1}, {-1, +1, -1}, {+1, -1, +1}, {+1, +1, -1}};
+constexpr size_t kChunk = 1u << 16; /* gates per launch: bounds the extracted-sample scratch to 2 x 270 MB */
+
+extern "C" int ieache_gate_batch_device(ieache_ctx *ctx, const ieache_cloudkey *key, int op, int32_t *out, const int32_t *a,
+                                        const int32_t *b, const int32_t *c, int32_t imm, size_t count)
+{
+    if (!ctx || !key || !out) return fail(IEACHE_ERR_ARG, "null argument");
+    if (key->ctx->device != ctx->device) return fail(IEACHE_ERR_ARG, "key lives on another device");
+    if (count == 0) return IEACHE_OK;
+    CU(cudaSetDevice(ctx->device));
+    const int n = key->p.n, mu = key->dp.mu;
+    if (op == IEACHE_OP_CONST) { CU(launch_linear(out, nullptr, (int)count, kLweStride, n, 0, imm ? mu : -mu, ctx->stream)); ctx->launches++; return IEACHE_OK; }
+    if (!a) return fail(IEACHE_ERR_ARG, "null input a");
+    if (op == IEACHE_OP_COPY || op == IEACHE_OP_NOT) {
+        CU(launch_linear(out, a, (int)count, kLweStride, n, op == IEACHE_OP_NOT ? -1 : 1, 0, ctx->stream));
+        ctx->launches++;
+        return IEACHE_OK;
+    }
+    if (op < 0 || op > IEACHE_OP_MUX) return fail(IEACHE_ERR_ARG, "unknown op %d", op);
+    if (!b || (op == IEACHE_OP_MUX && !c)) return fail(IEACHE_ERR_ARG, "null input operand");
+    const size_t per = std::min(count, kChunk);
+    int rc = ensure(ctx, &ctx->d_ext, &ctx->ext_cap, per * kExtStride * (op == IEACHE_OP_MUX ? 2 : 1));
+    if (rc) return rc;
+    for (size_t off = 0; off < count; off += per) {
+        const size_t m = std::min(per, count - off);
+        GateAddr ga{};
+        ga.tmpl = nullptr; ga.ntempl = (int)m; ga.n_inst = 1; ga.inst_samples = 0; ga.stride = kLweStride;
+        const int32_t *pa = a + off * kLweStride, *pb = b + off * kLweStride;
+        int32_t *po = out + off * kLweStride;
+        if (op == IEACHE_OP_MUX) {
+            /* bootsMUX: u1 = BR((0,-mu)+a+b), u2 = BR((0,-mu)-a+c), out = KS((0,mu)+u1+u2) */
+            const int32_t *pc = c + off * kLweStride;
+            ga.uni = GateT{0, 0, 0, +1, +1, -1};
+            if ((rc = run_br(ctx, key, ga, pa, pb, 0))) return rc;
+            ga.uni = GateT{0, 0, 0, -1, +1, -1};
+            if ((rc = run_br(ctx, key, ga, pa, pc, (int)m))) return rc;
+            if ((rc = run_ks(ctx, key, ga, po, (int)m, mu))) return rc;
+        } else {
+            ga.uni = GateT{0, 0, 0, k_lin[op][1], k_lin[op][2], k_lin[op][0]};
+            if ((rc = run_br(ctx, key, ga, pa, pb, 0))) return rc;
+            if ((rc = run_ks(ctx, key, ga, po, 0, 0))) return rc;
+        }
+    }
+    return IEACHE_OK;
+}
+
+extern "C" int ieache_samples_to_device(ieache_ctx *ctx, int32_t *dev, const int32_t *host, size_t count, int32_t n)
+{
+    if (!ctx || !dev || !host) return fail(IEACHE_ERR_ARG, "null argument");
+    if (count == 0) return IEACHE_OK;
+    CU(cudaMemcpy2DAsync(dev, kLweStride * 4, host, (size_t)(n + 1) * 4, (size_t)(n + 1) * 4, count, cudaMemcpyHostToDevice, ctx->stream));
+    return IEACHE_OK;
+}
+extern "C" int ieache_samples_to_host(ieache_ctx *ctx, int32_t *host, const int32_t *dev, size_t count, int32_t n)
+{
+    if (!ctx || !dev || !host) return fail(IEACHE_ERR_ARG, "null argument");
+    if (count == 0) return IEACHE_OK;
+    CU(cudaMemcpy2DAsync(host, (size_t)(n + 1) * 4, dev, kLweStride * 4, (size_t)(n + 1) * 4, count, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return IEACHE_OK;
+}
+extern "C" int ieache_device_alloc(ieache_ctx *ctx, size_t bytes, void **out)
+{
+    if (!ctx || !out) return fail(IEACHE_ERR_ARG, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMalloc(out, bytes));
+    return IEACHE_OK;
+}
+extern "C" int ieache_device_free(ieache_ctx *ctx, void *ptr)
+{
+    if (!ctx) return fail(IEACHE_ERR_ARG, "null ctx");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaFree(ptr));
+    return IEACHE_OK;
+}
+
+extern "C" int ieache_gate_batch(ieache_ctx *ctx, const ieache_cloudkey *key, int op, int32_t *out, const int32_t *a,
+                                 const int32_t *b, const int32_t *c, int32_t imm, size_t count)
+{
+    if (!ctx || !key || !out) return fail(IEACHE_ERR_ARG, "null argument");
+    if (count == 0) return IEACHE_OK;
+    CU(cudaSetDevice(ctx->device));
+    const int n = key->p.n;
+    const int32_t *src[3] = {a, b, c};
+    int rc;
+    for (int i = 0; i < 4; i++)
+        if (i == 3 || src[i])
+            if ((rc = ensure(ctx, &ctx->d_stage[i], &ctx->stage_cap[i], count * kLweStride))) return rc;
+    for (int i = 0; i < 3; i++)
+        if (src[i] && (rc = ieache_samples_to_device(ctx, ctx->d_stage[i], src[i], count, n))) return rc;
+    rc = ieache_gate_batch_device(ctx, key, op, ctx->d_stage[3], a ? ctx->d_stage[0] : nullptr, b ? ctx->d_stage[1] : nullptr,
+                                  c ? ctx->d_stage[2] : nullptr, imm, count);
+    if (rc) return rc;
+    return ieache_samples_to_host(ctx, out, ctx->d_stage[3], count, n);
+}
+
+extern "C" int ieache_bootstrap_woks(ieache_ctx *ctx, const ieache_cloudkey *key, int32_t *ext_out, const int32_t *x, size_t count)
+{
+    if (!ctx || !key || !ext_out || !x) return fail(IEACHE_ERR_ARG, "null argument");
+    if (count == 0) return IEACHE_OK;
+    if (count > kChunk) return fail(IEACHE_ERR_ARG, "count > %zu", kChunk);
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure(ctx, &ctx->d_stage[0], &ctx->stage_cap[0], count * kLweStride))) return rc;
+    if ((rc = ensure(ctx, &ctx->d_ext, &ctx->ext_cap, count * kExtStride))) return rc;
+    if ((rc = ieache_samples_to_device(ctx, ctx->d_stage[0], x, count, key->p.n))) return rc;
+    GateAddr ga{};
+    ga.tmpl = nullptr; ga.ntempl = (int)count; ga.n_inst = 1; ga.stride = kLweStride;
+    ga.uni = GateT{0, -1, 0, +1, 0, 0};
+    if ((rc = run_br(ctx, key, ga, ctx->d_stage[0], ctx->d_stage[0], 0))) return rc;
+    CU(cudaMemcpy2DAsync(ext_out, 1025 * 4, ctx->d_ext, kExtStride * 4, 1025 * 4, count, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return IEACHE_OK;
+}
+extern "C" int ieache_keyswitch(ieache_ctx *ctx, const ieache_cloudkey *key, int32_t *out, const int32_t *ext, size_t count)
+{
+    if (!ctx || !key || !out || !ext) return fail(IEACHE_ERR_ARG, "null argument");
+    if (count == 0) return IEACHE_OK;
+    if (count > kChunk) return fail(IEACHE_ERR_ARG, "count > %zu", kChunk);
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure(ctx, &ctx->d_stage[3], &ctx->stage_cap[3], count * kLweStride))) return rc;
+    if ((rc = ensure(ctx, &ctx->d_ext, &ctx->ext_cap, count * kExtStride))) return rc;
+    CU(cudaMemcpy2DAsync(ctx->d_ext, kExtStride * 4, ext, 1025 * 4, 1025 * 4, count, cudaMemcpyHostToDevice, ctx->stream));
+    GateAddr ga{};
+    ga.tmpl = nullptr; ga.ntempl = (int)count; ga.n_inst = 1; ga.stride = kLweStride;
+    if ((rc = run_ks(ctx, key, ga, ctx->d_stage[3], 0, 0))) return rc;
+    return ieache_samples_to_host(ctx, out, ctx->d_stage[3], count, key->p.n);
+}
+
+/* ------------------------------------------------------------------ circuits */
+struct ieache_circuit {
+    Circuit c;
+    /* device copies of the level templates, per device, created lazily */
+    int device = -1;
+    GateT *d_tmpl = nullptr;
+    std::vector<size_t> level_off;
+    GateT *d_out_refs = nullptr; /* unused for now */
+};
+
+extern "C" int ieache_circuit_build(int kind, int width, ieache_circuit **out)
+{
+    if (!out) return fail(IEACHE_ERR_ARG, "null out");
+    std::unique_ptr<ieache_circuit> c(new ieache_circuit());
+    if (!build_circuit(kind, width, c->c)) return fail(IEACHE_ERR_UNSUPPORTED, "no circuit for kind %d at width %d", kind, width);
+    *out = c.release();
+    return IEACHE_OK;
+}
+extern "C" void ieache_circuit_destroy(ieache_circuit *c)
+{
+    if (!c) return;
+    if (c->d_tmpl) { cudaSetDevice(c->device); cudaFree(c->d_tmpl); }
+    delete c;
+}
+extern "C" int ieache_circuit_stats(const ieache_circuit *c, uint64_t *bootstraps, uint64_t *and_gates, uint64_t *xor_gates,
+                                    uint32_t *levels, uint32_t *max_width, uint32_t *n_inputs, uint32_t *n_outputs)
+{
+    if (!c) return fail(IEACHE_ERR_ARG, "null circuit");
+    if (bootstraps) *bootstraps = c->c.gates.size();
+    if (and_gates) *and_gates = c->c.n_and;
+    if (xor_gates) *xor_gates = c->c.n_xor;
+    if (levels) *levels = (uint32_t)c->c.levels.size();
+    if (max_width) *max_width = c->c.max_width;
+    if (n_inputs) *n_inputs = (uint32_t)c->c.n_inputs;
+    if (n_outputs) *n_outputs = (uint32_t)c->c.outputs.size();
+    return IEACHE_OK;
+}
+
+static int circuit_upload(ieache_ctx *ctx, ieache_circuit *c)
+{
+    if (c->d_tmpl && c->device == ctx->device) return IEACHE_OK;
+    if (c->d_tmpl) { cudaSetDevice(c->device); cudaFree(c->d_tmpl); c->d_tmpl = nullptr; }
+    CU(cudaSetDevice(ctx->device));
+    std::vector<GateT> all;
+    c->level_off.clear();
+    for (const Level &lv : c->c.levels) { c->level_off.push_back(all.size()); all.insert(all.end(), lv.tmpl.begin(), lv.tmpl.end()); }
+    CU(cudaMalloc((void **)&c->d_tmpl, all.size() * sizeof(GateT)));
+    CU(cudaMemcpy(c->d_tmpl, all.data(), all.size() * sizeof(GateT), cudaMemcpyHostToDevice));
+    c->device = ctx->device;
+    return IEACHE_OK;
+}
+
+extern "C" int ieache_circuit_eval_device(ieache_ctx *ctx, const ieache_cloudkey *key, const ieache_circuit *cc, const int32_t *inputs,
+                                          int32_t *outputs, size_t n_expr)
+{
+    if (!ctx || !key || !cc || !inputs || !outputs) return fail(IEACHE_ERR_ARG, "null argument");
+    if (n_expr == 0) return IEACHE_OK;
+    ieache_circuit *c = const_cast<ieache_circuit *>(cc);
+    int rc = circuit_upload(ctx, c);
+    if (rc) return rc;
+    const Circuit &C = c->c;
+    const int n = key->p.n;
+    /* instances per pass, bounded by the wire memory budget (8 GiB) and the scratch for one level */
+    const size_t bytes_per_inst = (size_t)C.n_slots * kLweStride * 4;
+    size_t per = std::max<size_t>(1, std::min<size_t>(n_expr, (8ull << 30) / bytes_per_inst));
+    per = std::max<size_t>(1, std::min<size_t>(per, (size_t)(1u << 20) / std::max<uint32_t>(1, C.max_width)));
+    if ((rc = ensure(ctx, &ctx->d_wires, &ctx->wires_cap, per * C.n_slots * kLweStride))) return rc;
+    if ((rc = ensure(ctx, &ctx->d_ext, &ctx->ext_cap, per * C.max_width * kExtStride))) return rc;
+    /* output slot table (sign folded: outputs of cloud.c circuits are never negated refs) */
+    std::vector<int32_t> out_slots(C.outputs.size());
+    for (size_t i = 0; i < C.outputs.size(); i++) {
+        if (C.outputs[i].neg) return fail(IEACHE_ERR_UNSUPPORTED, "negated output reference");
+        out_slots[i] = C.slot_of_wire[C.outputs[i].wire];
+    }
+    int32_t *d_out_slots = nullptr;
+    CU(cudaMalloc((void **)&d_out_slots, out_slots.size() * 4));
+    CU(cudaMemcpyAsync(d_out_slots, out_slots.data(), out_slots.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    for (size_t off = 0; off < n_expr; off += per) {
+        const int m = (int)std::min(per, n_expr - off);
+        CU(launch_circuit_scatter_inputs(ctx->d_wires, inputs + off * C.n_inputs * kLweStride, m, C.n_inputs, C.n_slots, n, key->dp.mu, ctx->stream));
+        ctx->launches++;
+        for (size_t L = 0; L < C.levels.size(); L++) {
+            GateAddr ga{};
+            ga.tmpl = c->d_tmpl + c->level_off[L];
+            ga.ntempl = (int)C.levels[L].tmpl.size();
+            ga.n_inst = m; ga.inst_samples = C.n_slots; ga.stride = kLweStride;
+            if ((rc = run_br(ctx, key, ga, ctx->d_wires, ctx->d_wires, 0))) { cudaFree(d_out_slots); return rc; }
+            if ((rc = run_ks(ctx, key, ga, ctx->d_wires, 0, 0))) { cudaFree(d_out_slots); return rc; }
+        }
+        CU(launch_circuit_gather_outputs(outputs + off * C.outputs.size() * kLweStride, ctx->d_wires, d_out_slots, m,
+                                         (int)C.outputs.size(), C.n_slots, n, ctx->stream));
+        ctx->launches++;
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_out_slots);
+    return IEACHE_OK;
+}
+
+extern "C" int ieache_circuit_eval(ieache_ctx *ctx, const ieache_cloudkey *key, const ieache_circuit *c, const int32_t *inputs,
+                                   int32_t *outputs, size_t n_expr)
+{
+    if (!ctx || !key || !c || !inputs || !outputs) return fail(IEACHE_ERR_ARG, "null argument");
+    if (n_expr == 0) return IEACHE_OK;
+    CU(cudaSetDevice(ctx->device));
+    const int n = key->p.n;
+    const size_t nin = (size_t)c->c.n_inputs * n_expr, nout = c->c.outputs.size() * n_expr;
+    int rc;
+    if ((rc = ensure(ctx, &ctx->d_stage[0], &ctx->stage_cap[0], nin * kLweStride))) return rc;
+    if ((rc = ensure(ctx, &ctx->d_stage[3], &ctx->stage_cap[3], nout * kLweStride))) return rc;
+    if ((rc = ieache_samples_to_device(ctx, ctx->d_stage[0], inputs, nin, n))) return rc;
+    if ((rc = ieache_circuit_eval_device(ctx, key, c, ctx->d_stage[0], ctx->d_stage[3], n_expr))) return rc;
+    return ieache_samples_to_host(ctx, outputs, ctx->d_stage[3], nout, n);
+}
+
+/* ------------------------------------------------------------------ Cloud node process contract */
+static int32_t dec32(const HostKeySet &k, const int32_t *blk)
+{
+    int32_t bits[32], v = 0;
+    sym_decrypt_bits(k, blk, 32, bits);
+    for (int i = 0; i < 32; i++) v |= bits[i] << i;
+    return v;
+}
+static void enc32(const HostKeySet &k, int32_t v, int32_t *blk)
+{
+    int32_t bits[32];
+    for (int i = 0; i < 32; i++) bits[i] = (v >> i) & 1;
+    sym_encrypt_bits(k, bits, 32, blk);
+}
+
+extern "C" int ieache_cloud_run(ieache_ctx *ctx, const char *dir, double *seconds)
+{
+    if (!ctx || !dir) return fail(IEACHE_ERR_ARG, "null argument");
+    const std::string d(dir);
+    std::string msg;
+    int rc;
+    /* cloud.c:656-663 */
+    ieache_cloudkey *key = nullptr;
+    if ((rc = ieache_cloudkey_load_file(ctx, (d + "/cloud.key").c_str(), &key))) return rc;
+    std::unique_ptr<ieache_cloudkey, void (*)(ieache_cloudkey *)> key_guard(key, ieache_cloudkey_destroy);
+    HostKeySet nbit;
+    if ((rc = read_keyset((d + "/nbit.key").c_str(), nbit, false, msg))) return fail(rc, "%s", msg.c_str());
+    if (!nbit.has_secret) return fail(IEACHE_ERR_FORMAT, "nbit.key holds no secret key");
+    const int n = key->p.n, nb = nbit.p.n;
+    if (nb != n) return fail(IEACHE_ERR_UNSUPPORTED, "nbit.key and cloud.key use different n (%d vs %d)", nb, n);
+    const size_t w = n + 1, B = 32 * w;
+    /* cloud.c:703-766: two client blocks of 11 x 32 samples */
+    std::vector<int32_t> data(704 * w);
+    {
+        FILE *f = fopen((d + "/cloud.data").c_str(), "rb");
+        if (!f) return fail(IEACHE_ERR_IO, "cannot open %s/cloud.data", dir);
+        rc = read_samples(f, n, data.data(), 704);
+        fclose(f);
+        if (rc) return fail(rc, "cloud.data: short read (expected 704 samples of %zu bytes)", sample_record_bytes(n));
+    }
+    int int_op = 0;                                                             /* cloud.c:770-773 */
+    {
+        FILE *f = fopen((d + "/operator.txt").c_str(), "r");
+        if (!f) return fail(IEACHE_ERR_IO, "cannot open %s/operator.txt", dir);
+        if (fscanf(f, "%d", &int_op) != 1) int_op = 0;
+        fclose(f);
+    }
+    const int32_t *neg1 = &data[0], *bit1 = &data[B], *carry1 = &data[10 * B], *neg2 = &data[11 * B], *bit2 = &data[12 * B];
+    const int32_t int_bit1 = dec32(nbit, bit1), int_bit2 = dec32(nbit, bit2);    /* cloud.c:709-746 */
+    int32_t n1 = dec32(nbit, neg1);
+    const int32_t n2 = dec32(nbit, neg2);                                        /* cloud.c:780-796 */
+    if (n1 == 2) n1 = 1;
+    const int32_t int_negative = n1 + n2;
+    const int32_t code = int_negative == 3 ? 4 : int_negative;                   /* cloud.c:812-821 */
+    std::vector<int32_t> answer(352 * w);
+    enc32(nbit, code, &answer[0]);
+    int32_t int_bit;
+    if (int_op == 4) {                                                           /* cloud.c:833-843 */
+        int_bit = std::max(int_bit1, int_bit2);
+        enc32(nbit, int_bit * 2, &answer[B]);
+    } else if (int_bit1 >= int_bit2) { int_bit = int_bit1; memcpy(&answer[B], bit1, B * 4); }
+    else { int_bit = int_bit2; memcpy(&answer[B], bit2, B * 4); }
+    size_t out_count = 64;
+    int exit_code = 0;
+    int kind = 0;
+    bool swap_ops = false;
+    if (int_op == 4 && int_bit >= 256) exit_code = 126;                          /* cloud.c:860-864 */
+    else if ((int_op == 1 && int_negative != 1 && int_negative != 2) || (int_op == 2 && (int_negative == 1 || int_negative == 2)))
+        kind = IEACHE_CIRC_ADD;                                                  /* cloud.c:870 */
+    else if (int_op == 2 || (int_op == 1 && (int_negative == 1 || int_negative == 2))) {
+        kind = IEACHE_CIRC_SUB;                                                  /* cloud.c:1194 */
+        swap_ops = !((int_op == 2 && int_negative == 0) || (int_op == 1 && int_negative == 2)); /* cloud.c:1196,1809 */
+    } else if (int_op == 4) kind = IEACHE_CIRC_MUL;                              /* cloud.c:2368 */
+    double secs = 0;
+    if (kind) {
+        ieache_circuit *circ = nullptr;
+        if (ieache_circuit_build(kind, int_bit, &circ) == IEACHE_OK) {
+            std::unique_ptr<ieache_circuit, void (*)(ieache_circuit *)> cg(circ, ieache_circuit_destroy);
+            const int nc = int_bit / 32;
+            std::vector<int32_t> in((size_t)circ->c.n_inputs * w), out(circ->c.outputs.size() * w);
+            const int32_t *op1 = &data[2 * B], *op2 = &data[13 * B];
+            memcpy(&in[0], swap_ops ? op2 : op1, (size_t)nc * B * 4);
+            memcpy(&in[(size_t)nc * B], swap_ops ? op1 : op2, (size_t)nc * B * 4);
+            memcpy(&in[(size_t)2 * nc * B], carry1, B * 4);
+            const auto t0 = std::chrono::steady_clock::now();
+            if ((rc = ieache_circuit_eval(ctx, key, circ, in.data(), out.data(), 1))) return rc;
+            secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            const size_t nres = circ->c.outputs.size() / 32;
+            for (size_t q = 0; q < 8; q++) memcpy(&answer[(2 + q) * B], q < nres ? &out[q * B] : carry1, B * 4);   /* cloud.c:899-916 */
+            memcpy(&answer[10 * B], carry1, B * 4);
+            out_count = 352;
+            printf("Computation Time: %lf[sec]\n", secs);                       /* cloud.c:896 */
+            if (kind == IEACHE_CIRC_MUL) {                                       /* cloud.c:2468-2471 */
+                FILE *t = fopen((d + "/averagestandard.txt").c_str(), "a");
+                if (t) { fprintf(t, "%lf\n", secs); fclose(t); }
+            }
+        }
+    }
+    if (seconds) *seconds = secs;
+    FILE *f = fopen((d + "/answer.data").c_str(), "wb");
+    if (!f) return fail(IEACHE_ERR_IO, "cannot write %s/answer.data", dir);
+    rc = write_samples(f, n, answer.data(), out_count, key->p.ks_stdev * key->p.ks_stdev);
+    fclose(f);
+    if (rc) return fail(rc, "short write on answer.data");
+    return exit_code;
+}

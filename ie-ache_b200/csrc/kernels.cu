@@ -1,0 +1,410 @@
+/*
+ * kernels.cu — sm_100a kernels of the gate-bootstrapping engine.
+ *
+ *   blind_rotate_kernel  fused: linear gate pre-combination -> modSwitch -> test-vector init ->
+ *                        n x { (X^abar-1)*ACC, gadget decomposition, (k+1)l forward transforms,
+ *                        pointwise MAC with BK_i, k+1 inverse transforms, ACC += } -> SampleExtract
+ *                        (replaces libtfhe tfhe_bootstrap_woKS_FFT reached from
+ *                        Cloud/cloud.c:30,32,38,40,43 — SURVEY.md §8 a14, App. A)
+ *   keyswitch_kernel     lweKeySwitch as a vectorised gather-accumulate over a compacted digit list
+ *   bk_fft_kernel        key load: coefficient BK -> transform-domain layout (libtfhe does this on
+ *                        the CPU inside new_tfheGateBootstrappingCloudKeySet_fromFile, Cloud/cloud.c:657)
+ *
+ * One 64-thread group owns one gate: ACC (8 KB), two exchange buffers (2 x 9 KB) and the
+ * mod-switched mask live in shared memory; the transform-domain accumulators (2 x 8 complex)
+ * live in registers.  Groups only use their own named barrier, so a CTA is just a container
+ * that makes neighbouring gates share BK_i lines in L1.
+ */
+#include "kernels.h"
+#include "br_core.h"
+
+#include <math.h>
+
+namespace ieache {
+
+__device__ Tw d_tw2[8];
+__device__ Tw d_tw3[64];
+
+cudaError_t upload_twiddles()
+{
+    Tw tw2[8], tw3[64];
+    host_twiddles(tw2, tw3);
+    cudaError_t e = cudaMemcpyToSymbol(d_tw2, tw2, sizeof(tw2));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(d_tw3, tw3, sizeof(tw3));
+}
+
+__device__ __forceinline__ void group_sync(int grp)
+{
+    asm volatile("bar.sync %0, 64;" ::"r"(grp + 1) : "memory");
+}
+
+/* forward transform of the 8 points in registers; leaves evaluations in x[r] of thread t3 = tid */
+__device__ __forceinline__ void fwd_transform(double (&xr)[8], double (&xi)[8], cd *buf, int tid, int grp,
+                                              const Tw &w1, const Tw &w2, const Tw &w3)
+{
+    pass_fwd(xr, xi, w1);
+    st_pass1(buf, tid, xr, xi);
+    group_sync(grp);
+    ld_pass2(buf, tid, xr, xi);
+    pass_fwd(xr, xi, w2);
+    st_pass2(buf, tid, xr, xi);
+    group_sync(grp);
+    ld_pass3(buf, tid, xr, xi);
+    pass_fwd(xr, xi, w3);
+}
+/* inverse (x512): evaluations in x[r] -> z[tid+64m] in x[m] */
+__device__ __forceinline__ void inv_transform(double (&xr)[8], double (&xi)[8], cd *buf, int tid, int grp,
+                                              const Tw &w1, const Tw &w2, const Tw &w3)
+{
+    pass_inv(xr, xi, w3);
+    st_ipass3(buf, tid, xr, xi);
+    group_sync(grp);
+    ld_ipass2(buf, tid, xr, xi);
+    pass_inv(xr, xi, w2);
+    st_ipass2(buf, tid, xr, xi);
+    group_sync(grp);
+    ld_ipass1(buf, tid, xr, xi);
+    pass_inv(xr, xi, w1);
+}
+
+/* ------------------------------------------------------------------ key load */
+__global__ void __launch_bounds__(64) bk_fft_kernel(const int32_t *__restrict__ coef, double2 *__restrict__ out, int npoly)
+{
+    __shared__ cd buf[kBufElems];
+    const int q = blockIdx.x, tid = threadIdx.x;
+    if (q >= npoly) return;
+    const int32_t *p = coef + (size_t)q * kN;
+    double xr[8], xi[8];
+#pragma unroll
+    for (int m = 0; m < 8; m++) { xr[m] = (double)p[tid + 64 * m]; xi[m] = (double)p[tid + 64 * m + 512]; }
+    const Tw w1 = tw_pass1(), w2 = d_tw2[tid >> 3], w3 = d_tw3[tid];
+    fwd_transform(xr, xi, buf, tid, 0, w1, w2, w3);
+    double2 *o = out + (size_t)q * kHalfN;
+    const double sc = 1.0 / 512.0;
+#pragma unroll
+    for (int r = 0; r < 8; r++) o[r * 64 + tid] = make_double2(xr[r] * sc, xi[r] * sc);
+}
+
+cudaError_t launch_bk_fft(const int32_t *bk_coef, double2 *bkfft, int npoly, cudaStream_t s)
+{
+    bk_fft_kernel<<<npoly, 64, 0, s>>>(bk_coef, bkfft, npoly);
+    return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------ blind rotation */
+constexpr int kAccBytes = 2 * kN * 4;
+constexpr int kBufBytes = kBufElems * 16;
+constexpr int kAbarBytes = 2080;
+constexpr int kGroupSmem = kAccBytes + 2 * kBufBytes + kAbarBytes; /* 28704 */
+
+template <int L, int G>
+__global__ void __launch_bounds__(64 * G)
+blind_rotate_kernel(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
+                    const int32_t *__restrict__ baseB, int32_t *__restrict__ ext)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int grp = threadIdx.x >> 6, tid = threadIdx.x & 63;
+    const int g = blockIdx.x * G + grp;
+    if (g >= ga.ntempl * ga.n_inst) return; /* whole group leaves; groups never share a barrier */
+
+    unsigned char *base = smem_raw + (size_t)grp * kGroupSmem;
+    int32_t *acc = reinterpret_cast<int32_t *>(base);
+    cd *bufA = reinterpret_cast<cd *>(base + kAccBytes);
+    cd *bufB = reinterpret_cast<cd *>(base + kAccBytes + kBufBytes);
+    uint16_t *abar = reinterpret_cast<uint16_t *>(base + kAccBytes + 2 * kBufBytes);
+
+    const int n = p.n;
+    /* 1. linear pre-combination + modSwitch to Z_{2N} */
+    {
+        const int e = g / ga.ntempl, t = g - e * ga.ntempl;
+        GateT gt = ga.uni;
+        if (ga.tmpl) gt = ga.tmpl[t]; else { gt.in0 = (gt.in0 >= 0) ? t : -1; gt.in1 = (gt.in1 >= 0) ? t : -1; }
+        const size_t blk = (size_t)e * ga.inst_samples;
+        const int32_t *in0 = gt.in0 >= 0 ? baseA + (blk + gt.in0) * ga.stride : nullptr;
+        const int32_t *in1 = gt.in1 >= 0 ? baseB + (blk + gt.in1) * ga.stride : nullptr;
+        const int32_t c0 = gt.c0, c1 = gt.c1, cst = gt.cst_mu * p.mu;
+        for (int i = tid; i <= n; i += 64) {
+            int32_t v = (i == n) ? cst : 0;
+            if (in0) v += c0 * __ldg(in0 + i);
+            if (in1) v += c1 * __ldg(in1 + i);
+            abar[i] = (uint16_t)modswitch_2N(v);
+        }
+    }
+    group_sync(grp);
+    /* 2. ACC = (0, X^{2N-bbar} * mu * (1 + X + ... + X^{N-1})) */
+    {
+        const int bbar = abar[n];
+        const int a = (2 * kN - bbar) & (2 * kN - 1);
+        const int ar = a & (kN - 1);
+        const bool flip = a >= kN;
+        for (int j = tid; j < kN; j += 64) {
+            acc[j] = 0;
+            acc[kN + j] = ((j < ar) != flip) ? -p.mu : p.mu;
+        }
+    }
+    group_sync(grp);
+
+    const Tw w1 = tw_pass1();
+    const Tw w2 = d_tw2[tid >> 3];
+    const Tw w3 = d_tw3[tid];
+    const int Bgbit = p.Bgbit;
+    const uint32_t maskBg = (1u << Bgbit) - 1;
+    const int32_t halfBg = 1 << (Bgbit - 1);
+    uint32_t offset = 0;
+#pragma unroll
+    for (int i = 1; i <= L; i++) offset += (uint32_t)halfBg << (32 - i * Bgbit);
+
+    constexpr int kRowElems = 2 * kHalfN;        /* one BK row: 2 output polys x 512 points */
+    constexpr int kBkStride = 2 * L * kRowElems; /* elements per BK_i */
+    int toggle = 0;
+
+    /* 3. n CMux steps */
+    for (int i = 0; i < n; i++) {
+        const int a = abar[i];
+        if (a == 0) continue; /* uniform inside the group */
+        double sr[2][8], si[2][8];
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+            for (int r = 0; r < 8; r++) { sr[j][r] = 0.0; si[j][r] = 0.0; }
+        const double2 *bk_i = bkfft + (size_t)i * kBkStride + tid;
+
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            int32_t c[16];
+            rot_minus_one(acc + q * kN, tid, a, c);
+#pragma unroll
+            for (int pp = 0; pp < L; pp++) {
+                const int shift = 32 - (pp + 1) * Bgbit;
+                double xr[8], xi[8];
+#pragma unroll
+                for (int m = 0; m < 8; m++) {
+                    xr[m] = digit_f64(c[m], offset, shift, maskBg, halfBg);
+                    xi[m] = digit_f64(c[8 + m], offset, shift, maskBg, halfBg);
+                }
+                cd *buf = toggle ? bufB : bufA;
+                toggle ^= 1;
+                fwd_transform(xr, xi, buf, tid, grp, w1, w2, w3);
+                const double2 *bk_r = bk_i + (size_t)(q * L + pp) * kRowElems;
+#pragma unroll
+                for (int j = 0; j < 2; j++)
+#pragma unroll
+                    for (int r = 0; r < 8; r++) {
+                        const double2 b = __ldg(bk_r + j * kHalfN + r * 64);
+                        cmac(sr[j][r], si[j][r], xr[r], xi[r], b.x, b.y);
+                    }
+            }
+        }
+        /* inverse transforms and ACC update */
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            cd *buf = toggle ? bufB : bufA;
+            toggle ^= 1;
+            inv_transform(sr[j], si[j], buf, tid, grp, w1, w2, w3);
+            int32_t *accj = acc + j * kN;
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                accj[tid + 64 * m] += round_to_torus(sr[j][m]);
+                accj[tid + 64 * m + 512] += round_to_torus(si[j][m]);
+            }
+        }
+        group_sync(grp);
+    }
+
+    /* 4. SampleExtract at index 0 */
+    int32_t *o = ext + (size_t)g * kExtStride;
+    for (int j = tid; j < kN; j += 64) o[j] = (j == 0) ? acc[0] : -acc[kN - j];
+    if (tid == 0) o[kN] = acc[kN];
+}
+
+constexpr int kGroupsPerCta = 2;
+int blind_rotate_groups_per_cta() { return kGroupsPerCta; }
+int blind_rotate_smem_bytes(int groups) { return groups * kGroupSmem; }
+
+cudaError_t launch_blind_rotate(const DevParams &p, const double2 *bkfft, const GateAddr &ga, const int32_t *baseA,
+                                const int32_t *baseB, int32_t *ext, int ext_base, cudaStream_t s)
+{
+    const long long count = (long long)ga.ntempl * ga.n_inst;
+    if (count <= 0) return cudaSuccess;
+    ext += (size_t)ext_base * kExtStride;
+    constexpr int G = kGroupsPerCta;
+    const int smem = G * kGroupSmem;
+    const int grid = (int)((count + G - 1) / G);
+    cudaError_t e;
+    if (p.l == 3) {
+        e = cudaFuncSetAttribute(blind_rotate_kernel<3, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        blind_rotate_kernel<3, G><<<grid, 64 * G, smem, s>>>(p, bkfft, ga, baseA, baseB, ext);
+    } else if (p.l == 2) {
+        e = cudaFuncSetAttribute(blind_rotate_kernel<2, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        blind_rotate_kernel<2, G><<<grid, 64 * G, smem, s>>>(p, bkfft, ga, baseA, baseB, ext);
+    } else {
+        return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------ key switch */
+constexpr int kKsThreads = 160; /* 158 int4 lanes cover a 632-word row */
+constexpr int kKsMaxRows = 1024 * 16;
+
+__global__ void __launch_bounds__(kKsThreads)
+keyswitch_kernel(DevParams p, const int32_t *__restrict__ ksk, GateAddr ga, int32_t *__restrict__ out_base,
+                 const int32_t *__restrict__ ext, int pair_offset, int32_t cst_post)
+{
+    extern __shared__ __align__(16) unsigned char ks_smem[];
+    int32_t *rows = reinterpret_cast<int32_t *>(ks_smem); /* compacted row indices */
+    __shared__ int s_nrows;
+    const int g = blockIdx.x, tid = threadIdx.x;
+    if (g >= ga.ntempl * ga.n_inst) return;
+    const int e = g / ga.ntempl, tt = g - e * ga.ntempl;
+    const int out_idx = ga.tmpl ? ga.tmpl[tt].out : tt;
+    int32_t *outp = out_base + ((size_t)e * ga.inst_samples + out_idx) * ga.stride;
+    const int t = p.ks_t, basebit = p.ks_basebit, basem1 = (1 << basebit) - 1;
+    const uint32_t prec_offset = 1u << (32 - (1 + basebit * t));
+    const int32_t *u0 = ext + (size_t)g * kExtStride;
+    const int32_t *u1 = pair_offset > 0 ? ext + ((size_t)g + pair_offset) * kExtStride : nullptr;
+    if (tid == 0) s_nrows = 0;
+    __syncthreads();
+    for (int i = tid; i < kN; i += kKsThreads) {
+        uint32_t a = (uint32_t)u0[i];
+        if (u1) a += (uint32_t)u1[i];
+        a += prec_offset;
+        for (int j = 0; j < t; j++) {
+            const int d = (a >> (32 - (j + 1) * basebit)) & basem1;
+            if (d) {
+                const int slot = atomicAdd(&s_nrows, 1);
+                rows[slot] = (i * t + j) * basem1 + (d - 1);
+            }
+        }
+    }
+    __syncthreads();
+    const int nrows = s_nrows;
+    int4 accv = make_int4(0, 0, 0, 0);
+    if (tid < kLweStride / 4) {
+        const int4 *kv = reinterpret_cast<const int4 *>(ksk) + tid;
+        int r = 0;
+        for (; r + 8 <= nrows; r += 8) {
+            int4 v[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) v[q] = __ldg(kv + (size_t)rows[r + q] * (kLweStride / 4));
+#pragma unroll
+            for (int q = 0; q < 8; q++) { accv.x -= v[q].x; accv.y -= v[q].y; accv.z -= v[q].z; accv.w -= v[q].w; }
+        }
+        for (; r < nrows; r++) {
+            const int4 v = __ldg(kv + (size_t)rows[r] * (kLweStride / 4));
+            accv.x -= v.x; accv.y -= v.y; accv.z -= v.z; accv.w -= v.w;
+        }
+        /* b lives at word n of the row */
+        int32_t bval = u0[kN] + (u1 ? u1[kN] : 0) + cst_post;
+        const int w0 = tid * 4;
+        if (p.n >= w0 && p.n < w0 + 4) {
+            if (p.n == w0) accv.x += bval; else if (p.n == w0 + 1) accv.y += bval;
+            else if (p.n == w0 + 2) accv.z += bval; else accv.w += bval;
+        }
+        reinterpret_cast<int4 *>(outp)[tid] = accv;
+    }
+}
+
+cudaError_t launch_keyswitch(const DevParams &p, const int32_t *ksk, const GateAddr &ga, int32_t *out_base,
+                             const int32_t *ext, int pair_offset, int32_t cst_post, cudaStream_t s)
+{
+    const long long count = (long long)ga.ntempl * ga.n_inst;
+    if (count <= 0) return cudaSuccess;
+    const int smem = kN * p.ks_t * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(keyswitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    if (smem > 64 * 1024) return cudaErrorInvalidValue;
+    keyswitch_kernel<<<(unsigned)count, kKsThreads, smem, s>>>(p, ksk, ga, out_base, ext, pair_offset, cst_post);
+    return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------ small helpers */
+__global__ void linear_kernel(int32_t *out, const int32_t *a, int count, int stride, int n, int coef, int cst)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)count * stride;
+    if (idx >= total) return;
+    const int w = (int)(idx % stride);
+    int32_t v = 0;
+    if (w <= n) {
+        v = (a && coef) ? coef * a[idx] : 0;
+        if (w == n) v += cst;
+    }
+    out[idx] = v;
+}
+cudaError_t launch_linear(int32_t *out, const int32_t *a, int count, int stride, int n, int coef, int cst, cudaStream_t s)
+{
+    if (count <= 0) return cudaSuccess;
+    const size_t total = (size_t)count * stride;
+    linear_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(out, a, count, stride, n, coef, cst);
+    return cudaGetLastError();
+}
+
+__global__ void pack_ksk_kernel(const int32_t *__restrict__ src, int32_t *__restrict__ dst, int rows_in, int base, int n)
+{
+    /* one CTA per destination row */
+    const int row = blockIdx.x;            /* (i*t + j)*(base-1) + (d-1) */
+    const int ij = row / (base - 1), d = row % (base - 1) + 1;
+    const int32_t *s = src + ((size_t)ij * base + d) * (n + 1);
+    int32_t *o = dst + (size_t)row * kLweStride;
+    for (int w = threadIdx.x; w < kLweStride; w += blockDim.x) o[w] = (w <= n) ? s[w] : 0;
+    (void)rows_in;
+}
+cudaError_t launch_pack_ksk(const int32_t *src, int32_t *dst, int kNdim, int t, int base, int n, cudaStream_t s)
+{
+    const int rows = kNdim * t * (base - 1);
+    pack_ksk_kernel<<<rows, 128, 0, s>>>(src, dst, rows, base, n);
+    return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------ circuit wire blocks */
+/* instance block = [const0, const1, inputs..., gate slots...] of kLweStride-word samples */
+__global__ void circuit_scatter_kernel(int32_t *__restrict__ wires, const int32_t *__restrict__ inputs, int n_expr, int n_inputs,
+                                       int n_slots, int n, int32_t mu)
+{
+    const int per = n_inputs + 2;
+    const long long sample = blockIdx.x; /* (e, s) */
+    const int e = (int)(sample / per), s = (int)(sample % per);
+    if (e >= n_expr) return;
+    int32_t *dst = wires + ((size_t)e * n_slots + s) * kLweStride;
+    if (s < 2) {
+        for (int w = threadIdx.x; w < kLweStride; w += blockDim.x) dst[w] = (w == n) ? (s ? mu : -mu) : 0;
+    } else {
+        const int32_t *src = inputs + ((size_t)e * n_inputs + (s - 2)) * kLweStride;
+        for (int w = threadIdx.x; w < kLweStride; w += blockDim.x) dst[w] = src[w];
+    }
+}
+cudaError_t launch_circuit_scatter_inputs(int32_t *wires, const int32_t *inputs, int n_expr, int n_inputs, int n_slots, int n,
+                                          int32_t mu, cudaStream_t s)
+{
+    const long long blocks = (long long)n_expr * (n_inputs + 2);
+    circuit_scatter_kernel<<<(unsigned)blocks, 160, 0, s>>>(wires, inputs, n_expr, n_inputs, n_slots, n, mu);
+    return cudaGetLastError();
+}
+__global__ void circuit_gather_kernel(int32_t *__restrict__ outputs, const int32_t *__restrict__ wires,
+                                      const int32_t *__restrict__ out_slots, int n_expr, int n_outputs, int n_slots)
+{
+    const long long sample = blockIdx.x;
+    const int e = (int)(sample / n_outputs), o = (int)(sample % n_outputs);
+    if (e >= n_expr) return;
+    const int32_t *src = wires + ((size_t)e * n_slots + out_slots[o]) * kLweStride;
+    int32_t *dst = outputs + ((size_t)e * n_outputs + o) * kLweStride;
+    for (int w = threadIdx.x; w < kLweStride; w += blockDim.x) dst[w] = src[w];
+}
+cudaError_t launch_circuit_gather_outputs(int32_t *outputs, const int32_t *wires, const int32_t *out_slots, int n_expr,
+                                          int n_outputs, int n_slots, int n, cudaStream_t s)
+{
+    (void)n;
+    const long long blocks = (long long)n_expr * n_outputs;
+    circuit_gather_kernel<<<(unsigned)blocks, 160, 0, s>>>(outputs, wires, out_slots, n_expr, n_outputs, n_slots);
+    return cudaGetLastError();
+}
+
+} // namespace ieache

@@ -1,0 +1,143 @@
+/*
+ * ieache_b200.h — C ABI of the B200-native TFHE gate-bootstrapping engine for IE-ACHE's Cloud node.
+ *
+ * Plain pointers and sizes only (no C++ or torch types): this is what a ctypes replacement for
+ * Cloud/cloud_dynamic.py / Cloud/dragonfly_cipher_cloud.py:compute() binds, and
+ * what include/tfhe/tfhe.h (the libtfhe-compatible gate API cloud.c links against) is built on.
+ *
+ * Every compute entry point runs on the GPU; there is no CPU fallback.  All functions return
+ * IEACHE_OK (0) or a negative error code; ieache_last_error() gives the message of the last
+ * failure on the calling thread.
+ *
+ * An LWE sample is a record of (n+1) int32 words: a[0..n) then b  (libtfhe LweSample{a,b},
+ * SURVEY.md §8 a12).  Host arrays of samples are contiguous records; device arrays use a stride
+ * of IEACHE_DEVICE_STRIDE words.
+ */
+#ifndef IEACHE_B200_H
+#define IEACHE_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IEACHE_OK 0
+#define IEACHE_ERR_CUDA (-1)
+#define IEACHE_ERR_ARG (-2)
+#define IEACHE_ERR_IO (-3)
+#define IEACHE_ERR_FORMAT (-4)
+#define IEACHE_ERR_UNSUPPORTED (-5)
+#define IEACHE_ERR_NOMEM (-6)
+
+#define IEACHE_DEVICE_STRIDE 632 /* int32 words per LWE sample in device-resident arrays */
+
+/* gate opcodes (libtfhe boots* names; Cloud/cloud.c uses XOR, AND, NOT, COPY, CONSTANT) */
+enum ieache_op {
+    IEACHE_OP_NAND = 0, IEACHE_OP_OR = 1, IEACHE_OP_AND = 2, IEACHE_OP_XOR = 3, IEACHE_OP_XNOR = 4,
+    IEACHE_OP_NOR = 5, IEACHE_OP_ANDNY = 6, IEACHE_OP_ANDYN = 7, IEACHE_OP_ORNY = 8, IEACHE_OP_ORYN = 9,
+    IEACHE_OP_MUX = 10, IEACHE_OP_NOT = 11, IEACHE_OP_COPY = 12, IEACHE_OP_CONST = 13
+};
+
+/* new_default_gate_bootstrapping_parameters(110) = {630,1024,1,3,7,8,2,2^-15,2^-25,0.012467}
+ * (Keygen/keygen.c:22-23).  The engine reads these from the key, it does not assume them;
+ * the kernels support N = 1024, k = 1, l in {2,3}, n <= 631. */
+typedef struct ieache_params {
+    int32_t n, N, k, bk_l, bk_Bgbit, ks_t, ks_basebit, reserved;
+    double ks_stdev, bk_stdev, max_stdev;
+} ieache_params;
+
+typedef struct ieache_ctx ieache_ctx;           /* one per process and GPU */
+typedef struct ieache_cloudkey ieache_cloudkey; /* device-resident TFheGateBootstrappingCloudKeySet */
+typedef struct ieache_circuit ieache_circuit;   /* levelised gate DAG (Cloud/cloud.c circuits) */
+
+const char *ieache_last_error(void);
+const char *ieache_version(void);
+
+/* ---- context ---- */
+int ieache_ctx_create(int device, ieache_ctx **out);
+void ieache_ctx_destroy(ieache_ctx *ctx);
+int ieache_ctx_sync(ieache_ctx *ctx);
+/* number of engine kernels launched by this context so far (bench.py "gpu_launches") */
+uint64_t ieache_ctx_launch_count(const ieache_ctx *ctx);
+/* device time of the blind-rotation / key-switch kernels since the last reset, measured with
+ * CUDA events on the engine's stream (milliseconds) and number of launches timed */
+int ieache_ctx_kernel_times(ieache_ctx *ctx, double *blind_rotate_ms, double *keyswitch_ms,
+                            uint64_t *blind_rotate_launches, uint64_t *keyswitch_launches, int reset);
+int ieache_ctx_set_timing(ieache_ctx *ctx, int enabled);
+
+/* ---- cloud key: replaces new_tfheGateBootstrappingCloudKeySet_fromFile (Cloud/cloud.c:656-658) ---- */
+/* bk:  int32 [n][(k+1)l][k+1][N]  coefficient-domain TGSW samples (libtfhe bk->bk[i].all_sample[r].a[j])
+ * ksk: int32 [kN][t][2^basebit][n+1]  key-switch samples (libtfhe bk->ks->ks[i][j][d])
+ * The transform-domain copy (libtfhe bkFFT) is computed on the GPU. */
+int ieache_cloudkey_create(ieache_ctx *ctx, const ieache_params *p, const int32_t *bk, const int32_t *ksk,
+                           ieache_cloudkey **out);
+int ieache_cloudkey_load_file(ieache_ctx *ctx, const char *path, ieache_cloudkey **out);
+void ieache_cloudkey_destroy(ieache_cloudkey *key);
+int ieache_cloudkey_params(const ieache_cloudkey *key, ieache_params *out);
+/* device arrays of the key, for the one-time NCCL broadcast to the other GPUs */
+int ieache_cloudkey_device_arrays(const ieache_cloudkey *key, void **bkfft, size_t *bkfft_bytes, void **ksk,
+                                  size_t *ksk_bytes);
+/* bytes the arrays of a key with parameters p occupy on the device */
+int ieache_cloudkey_device_sizes(const ieache_params *p, size_t *bkfft_bytes, size_t *ksk_bytes);
+/* wrap arrays that already hold a key (filled by a broadcast); the caller keeps ownership */
+int ieache_cloudkey_adopt_device(ieache_ctx *ctx, const ieache_params *p, void *bkfft, void *ksk,
+                                 ieache_cloudkey **out);
+
+/* ---- batched gates: `count` independent boots<OP>(out[g], a[g], b[g] (, c[g])) ---- */
+/* host buffers, count x (n+1) words each; out may alias an input; b/c NULL where unused.
+ * For IEACHE_OP_CONST, a is NULL and imm is the plaintext bit. */
+int ieache_gate_batch(ieache_ctx *ctx, const ieache_cloudkey *key, int op, int32_t *out, const int32_t *a,
+                      const int32_t *b, const int32_t *c, int32_t imm, size_t count);
+/* device-resident buffers with stride IEACHE_DEVICE_STRIDE; asynchronous on the context stream */
+int ieache_gate_batch_device(ieache_ctx *ctx, const ieache_cloudkey *key, int op, int32_t *out, const int32_t *a,
+                             const int32_t *b, const int32_t *c, int32_t imm, size_t count);
+/* stages, for per-stage parity tests: pre-combined x -> extracted (kN+1 words, stride 1028 on device) */
+int ieache_bootstrap_woks(ieache_ctx *ctx, const ieache_cloudkey *key, int32_t *ext_out /*count x 1025*/,
+                          const int32_t *x /*count x (n+1)*/, size_t count);
+int ieache_keyswitch(ieache_ctx *ctx, const ieache_cloudkey *key, int32_t *out /*count x (n+1)*/,
+                     const int32_t *ext /*count x 1025*/, size_t count);
+
+/* device memory helpers for callers without a CUDA binding (ctypes) */
+int ieache_device_alloc(ieache_ctx *ctx, size_t bytes, void **out);
+int ieache_device_free(ieache_ctx *ctx, void *ptr);
+/* copy count samples between packed host records (n+1 words) and strided device records */
+int ieache_samples_to_device(ieache_ctx *ctx, int32_t *dev, const int32_t *host, size_t count, int32_t n);
+int ieache_samples_to_host(ieache_ctx *ctx, int32_t *host, const int32_t *dev, size_t count, int32_t n);
+
+/* ---- circuits of Cloud/cloud.c as levelised DAGs ---- */
+/* kinds: the dispatch of Cloud/cloud.c main() */
+enum ieache_circuit_kind {
+    IEACHE_CIRC_ADD = 1,      /* chained add()            cloud.c:870-1190 ; inputs A chunks, B chunks, carry */
+    IEACHE_CIRC_SUB = 2,      /* A - B via two's complement cloud.c:1194-1800 */
+    IEACHE_CIRC_MUL = 4,      /* mul32 / 2xmul64+split / 4xmul128+15 adds  cloud.c:2368-2719 */
+    IEACHE_CIRC_MULADD = 5    /* a*b+c: mul32 then 64-bit add (BASELINE.json config 3) */
+};
+/* width in bits of each operand: 32, 64, 128 or 256 (MUL: 32, 64, 128; MULADD: 32) */
+int ieache_circuit_build(int kind, int width, ieache_circuit **out);
+void ieache_circuit_destroy(ieache_circuit *c);
+/* statistics checked against SURVEY.md App. B */
+int ieache_circuit_stats(const ieache_circuit *c, uint64_t *bootstraps, uint64_t *and_gates, uint64_t *xor_gates,
+                         uint32_t *levels, uint32_t *max_width, uint32_t *n_inputs, uint32_t *n_outputs);
+/* evaluate n_expr independent instances, level by level, one blind-rotation launch and one
+ * key-switch launch per level over all instances.
+ * inputs : host, [n_expr][n_inputs][n+1]; outputs: host, [n_expr][n_outputs][n+1]
+ * Input order: operand-1 chunks (32 samples each, LSB first), operand-2 chunks, (MULADD: operand-3
+ * chunk,) then the 32-sample carry block of operand 1 (only sample 0 is read, cloud.c:24). */
+int ieache_circuit_eval(ieache_ctx *ctx, const ieache_cloudkey *key, const ieache_circuit *c, const int32_t *inputs,
+                        int32_t *outputs, size_t n_expr);
+/* same with device-resident inputs/outputs (stride IEACHE_DEVICE_STRIDE), asynchronous */
+int ieache_circuit_eval_device(ieache_ctx *ctx, const ieache_cloudkey *key, const ieache_circuit *c,
+                               const int32_t *inputs, int32_t *outputs, size_t n_expr);
+
+/* ---- the Cloud node's process contract (Cloud/cloud.c main()) ---- */
+/* Reads cloud.key, nbit.key, cloud.data, operator.txt in `dir`, writes answer.data (and appends
+ * averagestandard.txt on multiply).  Returns the exit code of ./cloud: 0, or 126 on the
+ * 256-bit-multiply abort path; negative on engine errors.  seconds (optional) receives the
+ * circuit time the reference prints as "Computation Time". */
+int ieache_cloud_run(ieache_ctx *ctx, const char *dir, double *seconds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,141 @@
+/*
+ * tests/emul/host_emul.cpp — TEST-ONLY host emulation of the blind-rotation kernel.
+ *
+ * Runs the exact per-thread arithmetic of ie-ache_b200/csrc/br_core.h (the same __host__
+ * __device__ functions the CUDA kernel calls) for the 64 threads of one group, phase by phase,
+ * with each barrier of the kernel becoming the end of a loop over threads.  It exists because
+ * the build container has no GPU: it lets the CPU test suite check the transform index math,
+ * the exchange-buffer layout, the BK layout and the decomposition against the oracle before a
+ * GPU run is spent.  It is NOT part of the product library and is never a fallback.
+ */
+#include "../../ie-ache_b200/csrc/br_core.h"
+
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+using namespace ieache;
+
+namespace {
+struct Regs { double xr[8], xi[8]; };
+
+struct Emul {
+    Tw w1, w2[8], w3[64];
+    Emul() { w1 = tw_pass1(); host_twiddles(w2, w3); }
+
+    void fwd(Regs *t, cd *buf) const
+    {
+        for (int tid = 0; tid < 64; tid++) { pass_fwd(t[tid].xr, t[tid].xi, w1); st_pass1(buf, tid, t[tid].xr, t[tid].xi); }
+        for (int tid = 0; tid < 64; tid++) ld_pass2(buf, tid, t[tid].xr, t[tid].xi);
+        for (int tid = 0; tid < 64; tid++) { pass_fwd(t[tid].xr, t[tid].xi, w2[tid >> 3]); st_pass2(buf, tid, t[tid].xr, t[tid].xi); }
+        for (int tid = 0; tid < 64; tid++) { ld_pass3(buf, tid, t[tid].xr, t[tid].xi); pass_fwd(t[tid].xr, t[tid].xi, w3[tid]); }
+    }
+    void inv(Regs *t, cd *buf) const
+    {
+        for (int tid = 0; tid < 64; tid++) { pass_inv(t[tid].xr, t[tid].xi, w3[tid]); st_ipass3(buf, tid, t[tid].xr, t[tid].xi); }
+        for (int tid = 0; tid < 64; tid++) ld_ipass2(buf, tid, t[tid].xr, t[tid].xi);
+        for (int tid = 0; tid < 64; tid++) { pass_inv(t[tid].xr, t[tid].xi, w2[tid >> 3]); st_ipass2(buf, tid, t[tid].xr, t[tid].xi); }
+        for (int tid = 0; tid < 64; tid++) { ld_ipass1(buf, tid, t[tid].xr, t[tid].xi); pass_inv(t[tid].xr, t[tid].xi, w1); }
+    }
+};
+const Emul &emul() { static Emul e; return e; }
+} // namespace
+
+extern "C" {
+
+/* forward transform of one int32 polynomial into the device BK layout [r][t3] (re,im), scaled */
+void emul_poly_fft(const int32_t *coef, double *out /*512*2*/, double scale)
+{
+    const Emul &e = emul();
+    Regs t[64];
+    cd buf[kBufElems];
+    for (int tid = 0; tid < 64; tid++)
+        for (int m = 0; m < 8; m++) { t[tid].xr[m] = (double)coef[tid + 64 * m]; t[tid].xi[m] = (double)coef[tid + 64 * m + 512]; }
+    e.fwd(t, buf);
+    for (int tid = 0; tid < 64; tid++)
+        for (int r = 0; r < 8; r++) { out[2 * (r * 64 + tid)] = t[tid].xr[r] * scale; out[2 * (r * 64 + tid) + 1] = t[tid].xi[r] * scale; }
+}
+
+/* inverse of emul_poly_fft (x512 unnormalised, like the kernel) */
+void emul_poly_ifft(const double *in /*512*2*/, double *coef_out /*1024*/)
+{
+    const Emul &e = emul();
+    Regs t[64];
+    cd buf[kBufElems];
+    for (int tid = 0; tid < 64; tid++)
+        for (int r = 0; r < 8; r++) { t[tid].xr[r] = in[2 * (r * 64 + tid)]; t[tid].xi[r] = in[2 * (r * 64 + tid) + 1]; }
+    e.inv(t, buf);
+    for (int tid = 0; tid < 64; tid++)
+        for (int m = 0; m < 8; m++) { coef_out[tid + 64 * m] = t[tid].xr[m]; coef_out[tid + 64 * m + 512] = t[tid].xi[m]; }
+}
+
+/* evaluation index K (root psi^(4K+1)) held at slot [r][t3] */
+int emul_slot_to_K(int r, int t3) { return (t3 >> 3) + 8 * (t3 & 7) + 64 * brev3(r); }
+
+/* whole blind rotation + sample extract of one gate, as the kernel does it.
+ * bk_coef: [n][2l][2][1024] int32 ; x: n+1 words (already pre-combined) ; ext: 1025 words */
+void emul_blind_rotate(int n, int l, int Bgbit, int32_t mu, const int32_t *bk_coef, const int32_t *x, int32_t *ext)
+{
+    const Emul &e = emul();
+    const int kpl = 2 * l;
+    /* key load */
+    std::vector<double> bkfft((size_t)n * kpl * 2 * 1024);
+    for (long q = 0; q < (long)n * kpl * 2; q++) emul_poly_fft(bk_coef + (size_t)q * kN, &bkfft[(size_t)q * 1024], 1.0 / 512.0);
+
+    std::vector<int32_t> acc(2 * kN);
+    std::vector<int> abar(n + 1);
+    for (int i = 0; i <= n; i++) abar[i] = modswitch_2N(x[i]);
+    {
+        const int a = (2 * kN - abar[n]) & (2 * kN - 1), ar = a & (kN - 1);
+        const bool flip = a >= kN;
+        for (int j = 0; j < kN; j++) { acc[j] = 0; acc[kN + j] = ((j < ar) != flip) ? -mu : mu; }
+    }
+    const uint32_t maskBg = (1u << Bgbit) - 1;
+    const int32_t halfBg = 1 << (Bgbit - 1);
+    uint32_t offset = 0;
+    for (int i = 1; i <= l; i++) offset += (uint32_t)halfBg << (32 - i * Bgbit);
+
+    Regs t[64];
+    cd bufA[kBufElems], bufB[kBufElems];
+    int toggle = 0;
+    std::vector<double> sr(64 * 2 * 8), si(64 * 2 * 8);
+    for (int i = 0; i < n; i++) {
+        const int a = abar[i];
+        if (a == 0) continue;
+        std::fill(sr.begin(), sr.end(), 0.0); std::fill(si.begin(), si.end(), 0.0);
+        for (int q = 0; q < 2; q++) {
+            int32_t c[64][16];
+            for (int tid = 0; tid < 64; tid++) rot_minus_one(&acc[q * kN], tid, a, c[tid]);
+            for (int pp = 0; pp < l; pp++) {
+                const int shift = 32 - (pp + 1) * Bgbit;
+                for (int tid = 0; tid < 64; tid++)
+                    for (int m = 0; m < 8; m++) {
+                        t[tid].xr[m] = digit_f64(c[tid][m], offset, shift, maskBg, halfBg);
+                        t[tid].xi[m] = digit_f64(c[tid][8 + m], offset, shift, maskBg, halfBg);
+                    }
+                e.fwd(t, toggle ? bufB : bufA); toggle ^= 1;
+                const double *bk_r = &bkfft[(((size_t)i * kpl + q * l + pp) * 2) * 1024];
+                for (int tid = 0; tid < 64; tid++)
+                    for (int j = 0; j < 2; j++)
+                        for (int r = 0; r < 8; r++) {
+                            const double *b = bk_r + (size_t)j * 1024 + 2 * (r * 64 + tid);
+                            cmac(sr[(tid * 2 + j) * 8 + r], si[(tid * 2 + j) * 8 + r], t[tid].xr[r], t[tid].xi[r], b[0], b[1]);
+                        }
+            }
+        }
+        for (int j = 0; j < 2; j++) {
+            for (int tid = 0; tid < 64; tid++)
+                for (int r = 0; r < 8; r++) { t[tid].xr[r] = sr[(tid * 2 + j) * 8 + r]; t[tid].xi[r] = si[(tid * 2 + j) * 8 + r]; }
+            e.inv(t, toggle ? bufB : bufA); toggle ^= 1;
+            for (int tid = 0; tid < 64; tid++)
+                for (int m = 0; m < 8; m++) {
+                    acc[j * kN + tid + 64 * m] += round_to_torus(t[tid].xr[m]);
+                    acc[j * kN + tid + 64 * m + 512] += round_to_torus(t[tid].xi[m]);
+                }
+        }
+    }
+    for (int j = 0; j < kN; j++) ext[j] = (j == 0) ? acc[0] : -acc[kN - j];
+    ext[kN] = acc[kN];
+}
+
+} // extern "C"
