@@ -84,6 +84,7 @@ def lib() -> ctypes.CDLL:
     L.ieache_keyswitch.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]
     L.ieache_device_alloc.argtypes = [c_void_p, c_size_t, POINTER(c_void_p)]
     L.ieache_device_free.argtypes = [c_void_p, c_void_p]
+    L.ieache_device_copy.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t]
     L.ieache_samples_to_device.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_int32]
     L.ieache_samples_to_host.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_int32]
     L.ieache_circuit_build.argtypes = [c_int, c_int, POINTER(c_void_p)]
@@ -93,6 +94,12 @@ def lib() -> ctypes.CDLL:
     L.ieache_circuit_eval.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]
     L.ieache_circuit_eval_device.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]
     L.ieache_cloud_run.argtypes = [c_void_p, c_char_p, POINTER(c_double)]
+    L.ieache_keygen.argtypes = [c_void_p, POINTER(Params), c_uint64, POINTER(c_void_p), POINTER(c_void_p), c_void_p, c_void_p]
+    L.ieache_secretkey_import.argtypes = [c_void_p, POINTER(Params), c_void_p, c_void_p, POINTER(c_void_p)]
+    L.ieache_secretkey_export.argtypes = [c_void_p, c_void_p, c_void_p]
+    L.ieache_secretkey_destroy.argtypes = [c_void_p]
+    L.ieache_sym_encrypt_device.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_uint64]
+    L.ieache_sym_decrypt_device.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]
     _lib = L
     return L
 
@@ -148,6 +155,36 @@ class CloudKey:
             self._h = None
 
 
+class SecretKey:
+    """LWE + TLWE secret keys (host and device copies): the Keygen/Client/Output side of the protocol."""
+
+    def __init__(self, engine: "Engine", handle: c_void_p, params: Params):
+        self.engine, self._h, self.params = engine, handle, params
+
+    def export(self):
+        lwe = np.zeros(self.params.n, dtype=np.int32)
+        tlwe = np.zeros(1024, dtype=np.int32)
+        _check(lib().ieache_secretkey_export(self._h, _ptr(lwe), _ptr(tlwe)))
+        return lwe, tlwe
+
+    def encrypt_to_device(self, bits: np.ndarray, out_dev: int, seed: int):
+        """bootsSymEncrypt (Client1/alice.c:117) of a host bit array into device samples."""
+        b = np.ascontiguousarray(bits, dtype=np.int32)
+        _check(lib().ieache_sym_encrypt_device(self.engine._h, self._h, _ptr(b), len(b), c_void_p(out_dev), seed))
+
+    def decrypt_from_device(self, samples_dev: int, count: int, want_phases: bool = False):
+        """bootsSymDecrypt (Output/verif.c:93) of device samples -> bits (and phases)."""
+        bits = np.zeros(count, dtype=np.int32)
+        ph = np.zeros(count, dtype=np.int32) if want_phases else None
+        _check(lib().ieache_sym_decrypt_device(self.engine._h, self._h, c_void_p(samples_dev), count, _ptr(bits), _ptr(ph)))
+        return (bits, ph) if want_phases else bits
+
+    def close(self):
+        if self._h:
+            lib().ieache_secretkey_destroy(self._h)
+            self._h = None
+
+
 class Engine:
     """One engine context per process and GPU."""
 
@@ -176,6 +213,23 @@ class Engine:
         h = c_void_p()
         _check(lib().ieache_cloudkey_adopt_device(self._h, byref(params), c_void_p(bkfft_dev), c_void_p(ksk_dev), byref(h)))
         return CloudKey(self, h)
+
+    def keygen(self, params: Params, seed: int, export: bool = False):
+        """Keygen/keygen.c on the GPU: returns (SecretKey, CloudKey[, bk_coef, ksk] when export)."""
+        sk, ck = c_void_p(), c_void_p()
+        bk = ks = None
+        if export:
+            bk = np.zeros(params.n * 2 * params.bk_l * 2 * 1024, dtype=np.int32)
+            ks = np.zeros(1024 * params.ks_t * (1 << params.ks_basebit) * (params.n + 1), dtype=np.int32)
+        _check(lib().ieache_keygen(self._h, byref(params), seed, byref(sk), byref(ck), _ptr(bk), _ptr(ks)))
+        out = (SecretKey(self, sk, params), CloudKey(self, ck))
+        return out + (bk, ks) if export else out
+
+    def secret_key_import(self, params: Params, lwe_key: np.ndarray, tlwe_key: np.ndarray | None = None) -> SecretKey:
+        h = c_void_p()
+        _check(lib().ieache_secretkey_import(self._h, byref(params), _ptr(np.ascontiguousarray(lwe_key, dtype=np.int32)),
+                                             _ptr(None if tlwe_key is None else np.ascontiguousarray(tlwe_key, dtype=np.int32)), byref(h)))
+        return SecretKey(self, h, params)
 
     # ---- gates ------------------------------------------------------------------------------
     def gate_batch(self, key: CloudKey, op, a=None, b=None, c=None, imm: int = 0, count: int | None = None) -> np.ndarray:
@@ -211,6 +265,9 @@ class Engine:
 
     def device_free(self, ptr: int):
         _check(lib().ieache_device_free(self._h, c_void_p(ptr)))
+
+    def device_copy(self, dst: int, src: int, nbytes: int):
+        _check(lib().ieache_device_copy(self._h, c_void_p(dst), c_void_p(src), nbytes))
 
     def samples_to_device(self, dev: int, host, count: int, n: int):
         _check(lib().ieache_samples_to_device(self._h, c_void_p(dev), _ptr(host), count, n))

@@ -19,6 +19,7 @@
 #include "../../include/ieache_b200.h"
 #include "circuit.h"
 #include "kernels.h"
+#include "keygen.h"
 #include "tfhe_io.h"
 
 using namespace ieache;
@@ -245,6 +246,116 @@ extern "C" int ieache_cloudkey_adopt_device(ieache_ctx *ctx, const ieache_params
     return IEACHE_OK;
 }
 
+/* ------------------------------------------------------------------ secret-key side on the GPU */
+struct ieache_secretkey {
+    ieache_ctx *ctx = nullptr;
+    ieache_params p{};
+    std::vector<int32_t> lwe_key, tlwe_key;
+    int32_t *d_lwe_key = nullptr, *d_tlwe_key = nullptr;
+};
+extern "C" void ieache_secretkey_destroy(ieache_secretkey *sk)
+{
+    if (!sk) return;
+    cudaSetDevice(sk->ctx->device);
+    cudaFree(sk->d_lwe_key); cudaFree(sk->d_tlwe_key);
+    delete sk;
+}
+extern "C" int ieache_secretkey_import(ieache_ctx *ctx, const ieache_params *p, const int32_t *lwe_key, const int32_t *tlwe_key,
+                                       ieache_secretkey **out)
+{
+    if (!ctx || !lwe_key || !out) return fail(IEACHE_ERR_ARG, "null argument");
+    int rc = check_params(p);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    std::unique_ptr<ieache_secretkey, void (*)(ieache_secretkey *)> sk(new ieache_secretkey(), ieache_secretkey_destroy);
+    sk->ctx = ctx; sk->p = *p;
+    sk->lwe_key.assign(lwe_key, lwe_key + p->n);
+    sk->tlwe_key.assign(1024, 0);
+    if (tlwe_key) sk->tlwe_key.assign(tlwe_key, tlwe_key + 1024);
+    CU(cudaMalloc((void **)&sk->d_lwe_key, kLweStride * 4));
+    CU(cudaMalloc((void **)&sk->d_tlwe_key, 1024 * 4));
+    CU(cudaMemset(sk->d_lwe_key, 0, kLweStride * 4));
+    CU(cudaMemcpy(sk->d_lwe_key, sk->lwe_key.data(), (size_t)p->n * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(sk->d_tlwe_key, sk->tlwe_key.data(), 1024 * 4, cudaMemcpyHostToDevice));
+    *out = sk.release();
+    return IEACHE_OK;
+}
+extern "C" int ieache_secretkey_export(const ieache_secretkey *sk, int32_t *lwe_key, int32_t *tlwe_key)
+{
+    if (!sk || !lwe_key) return fail(IEACHE_ERR_ARG, "null argument");
+    memcpy(lwe_key, sk->lwe_key.data(), sk->lwe_key.size() * 4);
+    if (tlwe_key) memcpy(tlwe_key, sk->tlwe_key.data(), sk->tlwe_key.size() * 4);
+    return IEACHE_OK;
+}
+extern "C" int ieache_keygen(ieache_ctx *ctx, const ieache_params *p, uint64_t seed, ieache_secretkey **sk_out, ieache_cloudkey **ck_out,
+                             int32_t *bk_export, int32_t *ksk_export)
+{
+    if (!ctx || !sk_out || !ck_out) return fail(IEACHE_ERR_ARG, "null argument");
+    int rc = check_params(p);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    std::vector<int32_t> lwe(p->n), tlwe(1024);
+    host_random_bits(seed, 1, lwe.data(), p->n);
+    host_random_bits(seed, 2, tlwe.data(), 1024);
+    ieache_secretkey *sk = nullptr;
+    if ((rc = ieache_secretkey_import(ctx, p, lwe.data(), tlwe.data(), &sk))) return rc;
+    std::unique_ptr<ieache_secretkey, void (*)(ieache_secretkey *)> skg(sk, ieache_secretkey_destroy);
+    std::unique_ptr<ieache_cloudkey, void (*)(ieache_cloudkey *)> key(new ieache_cloudkey(), ieache_cloudkey_destroy);
+    key->ctx = ctx; key->p = *p; fill_dev_params(*p, key->dp);
+    ieache_cloudkey_device_sizes(p, &key->bkfft_bytes, &key->ksk_bytes);
+    CU(cudaMalloc((void **)&key->bkfft, key->bkfft_bytes));
+    CU(cudaMalloc((void **)&key->ksk, key->ksk_bytes));
+    const int kpl = 2 * p->bk_l, base = 1 << p->ks_basebit;
+    const size_t bk_words = (size_t)p->n * kpl * 2 * 1024, ksk_words = (size_t)1024 * p->ks_t * base * (p->n + 1);
+    double2 *d_shat = nullptr;
+    int32_t *d_bk = nullptr, *d_ks = nullptr;
+    CU(cudaMalloc((void **)&d_shat, 512 * sizeof(double2)));
+    if (bk_export) CU(cudaMalloc((void **)&d_bk, bk_words * 4));
+    if (ksk_export) { CU(cudaMalloc((void **)&d_ks, ksk_words * 4)); CU(cudaMemsetAsync(d_ks, 0, ksk_words * 4, ctx->stream)); }
+    CU(launch_keygen(seed, key->dp, p->ks_stdev, p->bk_stdev, sk->d_lwe_key, sk->d_tlwe_key, d_shat, key->bkfft, key->ksk, d_bk, d_ks, ctx->stream));
+    ctx->launches += 3;
+    if (bk_export) CU(cudaMemcpyAsync(bk_export, d_bk, bk_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ksk_export) CU(cudaMemcpyAsync(ksk_export, d_ks, ksk_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_shat); cudaFree(d_bk); cudaFree(d_ks);
+    *sk_out = skg.release();
+    *ck_out = key.release();
+    return IEACHE_OK;
+}
+extern "C" int ieache_sym_encrypt_device(ieache_ctx *ctx, const ieache_secretkey *sk, const int32_t *bits, size_t count, int32_t *out_dev,
+                                         uint64_t seed)
+{
+    if (!ctx || !sk || !bits || !out_dev) return fail(IEACHE_ERR_ARG, "null argument");
+    if (count == 0) return IEACHE_OK;
+    CU(cudaSetDevice(ctx->device));
+    int32_t *d_bits = nullptr;
+    CU(cudaMalloc((void **)&d_bits, count * 4));
+    CU(cudaMemcpyAsync(d_bits, bits, count * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(launch_encrypt(seed, sk->p.n, sk->p.ks_stdev, 1 << 29, sk->d_lwe_key, d_bits, out_dev, (long long)count, ctx->stream));
+    ctx->launches++;
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_bits);
+    return IEACHE_OK;
+}
+extern "C" int ieache_sym_decrypt_device(ieache_ctx *ctx, const ieache_secretkey *sk, const int32_t *samples_dev, size_t count,
+                                         int32_t *bits, int32_t *phases)
+{
+    if (!ctx || !sk || !samples_dev || (!bits && !phases)) return fail(IEACHE_ERR_ARG, "null argument");
+    if (count == 0) return IEACHE_OK;
+    CU(cudaSetDevice(ctx->device));
+    int32_t *d_ph = nullptr;
+    CU(cudaMalloc((void **)&d_ph, count * 4));
+    CU(launch_phase(sk->p.n, sk->d_lwe_key, samples_dev, d_ph, (long long)count, ctx->stream));
+    ctx->launches++;
+    std::vector<int32_t> ph(count);
+    CU(cudaMemcpyAsync(ph.data(), d_ph, count * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_ph);
+    if (phases) memcpy(phases, ph.data(), count * 4);
+    if (bits) for (size_t i = 0; i < count; i++) bits[i] = ph[i] > 0 ? 1 : 0;
+    return IEACHE_OK;
+}
+
 /* ------------------------------------------------------------------ launches with optional timing */
 static int run_br(ieache_ctx *ctx, const ieache_cloudkey *key, const GateAddr &ga, const int32_t *A, const int32_t *B, int ext_base)
 {
@@ -334,6 +445,14 @@ extern "C" int ieache_device_alloc(ieache_ctx *ctx, size_t bytes, void **out)
     if (!ctx || !out) return fail(IEACHE_ERR_ARG, "null argument");
     CU(cudaSetDevice(ctx->device));
     CU(cudaMalloc(out, bytes));
+    return IEACHE_OK;
+}
+extern "C" int ieache_device_copy(ieache_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    if (!ctx || !dst || !src) return fail(IEACHE_ERR_ARG, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return IEACHE_OK;
 }
 extern "C" int ieache_device_free(ieache_ctx *ctx, void *ptr)

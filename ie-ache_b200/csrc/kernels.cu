@@ -34,6 +34,13 @@ cudaError_t upload_twiddles()
     return cudaMemcpyToSymbol(d_tw3, tw3, sizeof(tw3));
 }
 
+cudaError_t twiddle_ptrs(const Tw **tw2, const Tw **tw3)
+{
+    cudaError_t e = cudaGetSymbolAddress((void **)tw2, d_tw2);
+    if (e != cudaSuccess) return e;
+    return cudaGetSymbolAddress((void **)tw3, d_tw3);
+}
+
 __device__ __forceinline__ void group_sync(int grp)
 {
     asm volatile("bar.sync %0, 64;" ::"r"(grp + 1) : "memory");

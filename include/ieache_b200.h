@@ -84,6 +84,25 @@ int ieache_cloudkey_device_sizes(const ieache_params *p, size_t *bkfft_bytes, si
 int ieache_cloudkey_adopt_device(ieache_ctx *ctx, const ieache_params *p, void *bkfft, void *ksk,
                                  ieache_cloudkey **out);
 
+/* ---- secret-key side on the GPU: Keygen/keygen.c, Client1/alice.c:117, Output/verif.c:93 ---- */
+typedef struct ieache_secretkey ieache_secretkey; /* LWE key (n bits) + TLWE key (N bits), host and device copies */
+/* new_random_gate_bootstrapping_secret_keyset (Keygen/keygen.c:30-36): draws both secret keys from
+ * `seed` and builds the bootstrapping and key-switch keys directly in device layout.  If
+ * bk_export / ksk_export are non-NULL they receive the libtfhe-order coefficient arrays
+ * ([n][(k+1)l][k+1][N] and [kN][t][2^basebit][n+1]) so the key can be written to cloud.key. */
+int ieache_keygen(ieache_ctx *ctx, const ieache_params *p, uint64_t seed, ieache_secretkey **sk, ieache_cloudkey **ck,
+                  int32_t *bk_export, int32_t *ksk_export);
+int ieache_secretkey_import(ieache_ctx *ctx, const ieache_params *p, const int32_t *lwe_key, const int32_t *tlwe_key,
+                            ieache_secretkey **sk);
+int ieache_secretkey_export(const ieache_secretkey *sk, int32_t *lwe_key /*n*/, int32_t *tlwe_key /*N, may be NULL*/);
+void ieache_secretkey_destroy(ieache_secretkey *sk);
+/* bootsSymEncrypt of `count` bits (host array) into device samples (stride IEACHE_DEVICE_STRIDE) */
+int ieache_sym_encrypt_device(ieache_ctx *ctx, const ieache_secretkey *sk, const int32_t *bits, size_t count, int32_t *out_dev,
+                              uint64_t seed);
+/* bootsSymDecrypt of device samples: bits (phase > 0) and, optionally, the raw phases, to host arrays */
+int ieache_sym_decrypt_device(ieache_ctx *ctx, const ieache_secretkey *sk, const int32_t *samples_dev, size_t count,
+                              int32_t *bits, int32_t *phases);
+
 /* ---- batched gates: `count` independent boots<OP>(out[g], a[g], b[g] (, c[g])) ---- */
 /* host buffers, count x (n+1) words each; out may alias an input; b/c NULL where unused.
  * For IEACHE_OP_CONST, a is NULL and imm is the plaintext bit. */
@@ -101,6 +120,8 @@ int ieache_keyswitch(ieache_ctx *ctx, const ieache_cloudkey *key, int32_t *out /
 /* device memory helpers for callers without a CUDA binding (ctypes) */
 int ieache_device_alloc(ieache_ctx *ctx, size_t bytes, void **out);
 int ieache_device_free(ieache_ctx *ctx, void *ptr);
+/* device-to-device copy on the context stream, synchronous on return (key replication plumbing) */
+int ieache_device_copy(ieache_ctx *ctx, void *dst, const void *src, size_t bytes);
 /* copy count samples between packed host records (n+1 words) and strided device records */
 int ieache_samples_to_device(ieache_ctx *ctx, int32_t *dev, const int32_t *host, size_t count, int32_t n);
 int ieache_samples_to_host(ieache_ctx *ctx, int32_t *host, const int32_t *dev, size_t count, int32_t n);

@@ -254,6 +254,19 @@ static void keyset_build_fft(OKeySet *ks)
     }
 }
 
+static void keyset_build_fft(OKeySet *ks);
+OKeySet *o_keyset_from_arrays(const OParams *p, const int32_t *lwe_key, const int32_t *tlwe_key,
+                              const Torus32 *bk, const Torus32 *ksk)
+{
+    OKeySet *ks = keyset_alloc(p, lwe_key != NULL);
+    if (lwe_key) memcpy(ks->lwe_key, lwe_key, sizeof(int32_t) * p->n);
+    if (lwe_key && tlwe_key) memcpy(ks->tlwe_key, tlwe_key, sizeof(int32_t) * p->k * p->N);
+    memcpy(ks->bk, bk, sizeof(Torus32) * bk_words(p));
+    memcpy(ks->ksk, ksk, sizeof(Torus32) * ksk_words(p));
+    keyset_build_fft(ks);
+    return ks;
+}
+
 OKeySet *o_keygen(const OParams *p, uint64_t seed)
 {
     OKeySet *ks = keyset_alloc(p, 1);

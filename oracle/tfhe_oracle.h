@@ -54,6 +54,9 @@ void o_params_small(OParams *p, int32_t n_small);
 
 /* Keygen/keygen.c:30-36: one random secret key set (LWE key, TLWE key, BK, KSK). */
 OKeySet *o_keygen(const OParams *p, uint64_t seed);
+/* wrap externally generated key material (copied); lwe_key / tlwe_key may be NULL (cloud key only) */
+OKeySet *o_keyset_from_arrays(const OParams *p, const int32_t *lwe_key, const int32_t *tlwe_key,
+                              const Torus32 *bk, const Torus32 *ksk);
 void o_keyset_free(OKeySet *ks);
 const OParams *o_keyset_params(const OKeySet *ks);
 int o_keyset_has_secret(const OKeySet *ks);

@@ -35,6 +35,8 @@ def _lib():
         L = ctypes.CDLL(LIB)
         L.o_keygen.restype = c_void_p
         L.o_keygen.argtypes = [POINTER(OParams), c_uint64]
+        L.o_keyset_from_arrays.restype = c_void_p
+        L.o_keyset_from_arrays.argtypes = [POINTER(OParams), c_void_p, c_void_p, c_void_p, c_void_p]
         L.o_read_key.restype = c_void_p
         L.o_read_key.argtypes = [c_char_p]
         for f in ("o_lwe_key", "o_tlwe_key", "o_bk_coef", "o_ksk", "o_keyset_params"):
@@ -175,6 +177,9 @@ class KeySet:
 class Oracle:
     def keygen(self, p: OParams, seed: int) -> KeySet:
         return KeySet(_lib().o_keygen(byref(p), seed))
+
+    def from_arrays(self, p: OParams, lwe_key, tlwe_key, bk, ksk) -> KeySet:
+        return KeySet(_lib().o_keyset_from_arrays(byref(p), _vp(lwe_key), _vp(tlwe_key), _vp(bk), _vp(ksk)))
 
     def read_key(self, path: str) -> KeySet:
         h = _lib().o_read_key(path.encode())

@@ -1,0 +1,85 @@
+"""The blind-rotation kernel's per-thread code (ie-ache_b200/csrc/br_core.h) executed on the CPU by
+tests/emul/host_emul.cpp and compared with the oracle: transform layout, exactness of the negacyclic
+product, and a whole blind rotation + sample extraction."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import oracle_bind as ob
+
+EMUL = os.path.join(os.path.dirname(__file__), "emul", "libbr_emul.so")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    if not os.path.exists(EMUL):
+        pytest.fail("tests/emul/libbr_emul.so missing: run __graft_entry__.build()")
+    E = ctypes.CDLL(EMUL)
+    E.emul_slot_to_K.restype = ctypes.c_int
+    return E
+
+
+def vp(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def test_slot_order_is_evaluation_at_odd_roots(emul):
+    rng = np.random.default_rng(3)
+    a = rng.integers(-64, 64, 1024).astype(np.int32)
+    fa = np.zeros(1024)
+    emul.emul_poly_fft(vp(a), vp(fa), ctypes.c_double(1.0))
+    ca = fa[0::2] + 1j * fa[1::2]
+    psi = np.exp(1j * np.pi / 1024)
+    seen = set()
+    for r in range(8):
+        for t3 in (0, 9, 31, 63):
+            K = emul.emul_slot_to_K(r, t3)
+            seen.add(K)
+            x = psi ** (4 * K + 1)
+            val = np.polyval(a[::-1].astype(np.complex128), x)
+            assert abs(val - ca[r * 64 + t3]) < 1e-6
+    assert len(seen) == 32
+    assert sorted(emul.emul_slot_to_K(r, t) for r in range(8) for t in range(64)) == list(range(512))
+
+
+def test_negacyclic_product_is_exact(emul):
+    rng = np.random.default_rng(4)
+    a = rng.integers(-64, 64, 1024).astype(np.int32)           # gadget digits
+    b = rng.integers(-2 ** 31, 2 ** 31, 1024).astype(np.int32)  # torus coefficients
+    fa, fb = np.zeros(1024), np.zeros(1024)
+    emul.emul_poly_fft(vp(a), vp(fa), ctypes.c_double(1.0))
+    emul.emul_poly_fft(vp(b), vp(fb), ctypes.c_double(1.0 / 512))
+    prod = (fa[0::2] + 1j * fa[1::2]) * (fb[0::2] + 1j * fb[1::2])
+    pin = np.zeros(1024)
+    pin[0::2], pin[1::2] = prod.real, prod.imag
+    out = np.zeros(1024)
+    emul.emul_poly_ifft(vp(pin), vp(out))
+    full = np.convolve(a.astype(object), b.astype(object))
+    ref = [int(full[i]) - (int(full[i + 1024]) if i + 1024 < len(full) else 0) for i in range(1024)]
+    assert max(abs(out[i] - ref[i]) for i in range(1024)) < 0.25
+
+
+@pytest.mark.parametrize("n,l,bgbit", [(24, 3, 7), (12, 2, 10)])
+def test_blind_rotate_matches_oracle(emul, oracle, n, l, bgbit):
+    p = ob.params_default(n)
+    p.bk_l, p.bk_Bgbit = l, bgbit
+    ks = oracle.keygen(p, seed=777)
+    bits = np.array([1, 0, 1, 1, 0, 0], dtype=np.int32)
+    s = ks.encrypt(bits, 5)
+    mu = 1 << 29
+    bk = ks.bk_coef()
+    for g in range(6):
+        x = (s[g] + s[(g + 1) % 6]).astype(np.int32)
+        x[n] -= mu
+        ext_o = ks.bootstrap_woks(x[None])[0]
+        ext_e = np.zeros(1025, dtype=np.int32)
+        emul.emul_blind_rotate(n, l, bgbit, ctypes.c_int32(mu), vp(bk), vp(x), vp(ext_e))
+        want = int(bits[g] & bits[(g + 1) % 6])
+        ph = ks.phase_extracted(ext_e[None])[0]
+        assert (ph > 0) == bool(want)
+        d = ext_o.astype(np.int64) - ext_e.astype(np.int64)
+        d = ((d + 2 ** 31) % 2 ** 32) - 2 ** 31
+        assert np.abs(d).max() <= 2   # FP64 rounding may differ in the last unit; normally 0
+    ks.free()

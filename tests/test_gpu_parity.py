@@ -1,0 +1,296 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI of
+libieache_b200.so, against the CPU oracle on the same seeded inputs, against the committed golden
+vectors, and — at sizes the oracle cannot reach — against plain integer arithmetic and
+size-independent properties.
+
+Bar: decrypted bits identical; key switching (integer) bit-exact; per-gate output
+phase within 2^-10 of the torus of the oracle's (FFT rounding may flip a key-switch digit, which costs
+about one key-switch noise draw ~2^-15; the decision margin is 1/8)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_bind as ob
+
+pytestmark = pytest.mark.gpu
+
+PHASE_TOL = 1 << 22  # 2^-10 of the torus, in Torus32 units
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN_OPS = ["NAND", "OR", "AND", "XOR", "XNOR", "NOR", "ANDNY", "ANDYN", "ORNY", "ORYN"]
+
+
+def torus_dist(a, b):
+    d = a.astype(np.int64) - b.astype(np.int64)
+    return np.abs(((d + 2 ** 31) % 2 ** 32) - 2 ** 31)
+
+
+@pytest.fixture(scope="module")
+def eng(pkg):
+    e = pkg.Engine(0)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def full(pkg, oracle, eng):
+    """default parameters (n = 630): oracle key set + the same key on the GPU"""
+    ks = oracle.keygen(ob.params_default(630), seed=2024)
+    key = eng.cloud_key_from_arrays(pkg.Params.default(630), ks.bk_coef(), ks.ksk())
+    yield ks, key
+    key.close(); ks.free()
+
+
+@pytest.fixture(scope="module")
+def small(pkg, oracle, eng):
+    """n = 8: the oracle finishes whole multiplier circuits in seconds"""
+    ks = oracle.keygen(ob.params_default(8), seed=31)
+    nbit = oracle.keygen(ob.params_default(8), seed=32)
+    key = eng.cloud_key_from_arrays(pkg.Params.default(8), ks.bk_coef(), ks.ksk())
+    yield ks, nbit, key
+    key.close(); ks.free(); nbit.free()
+
+
+# ------------------------------------------------------------------ gates
+@pytest.mark.parametrize("op", BIN_OPS + ["MUX"])
+def test_gate_parity_default_params(eng, full, op):
+    ks, key = full
+    rng = np.random.default_rng(abs(hash(op)) % 1000)
+    ba, bb, bc = (rng.integers(0, 2, 16).astype(np.int32) for _ in range(3))
+    a, b, c = ks.encrypt(ba, 1), ks.encrypt(bb, 2), ks.encrypt(bc, 3)
+    got = eng.gate_batch(key, op, a, b, c if op == "MUX" else None)
+    want = ks.gate_batch(ob.OPS[op], a, b, c if op == "MUX" else None)
+    assert (ks.decrypt(got) == ks.decrypt(want)).all()
+    assert torus_dist(ks.phase(got), ks.phase(want)).max() < PHASE_TOL
+
+
+def test_free_gates_are_exact(eng, full):
+    ks, key = full
+    a = ks.encrypt([0, 1, 1, 0], 9)
+    assert (eng.gate_batch(key, "NOT", a) == ks.gate_batch(ob.OPS["NOT"], a)).all()
+    assert (eng.gate_batch(key, "COPY", a) == a).all()
+    c1 = eng.gate_batch(key, "CONST", imm=1, count=3)
+    assert (c1[:, :630] == 0).all() and (c1[:, 630] == 1 << 29).all()
+    c0 = eng.gate_batch(key, "CONST", imm=0, count=2)
+    assert (c0[:, 630] == -(1 << 29)).all()
+
+
+def test_golden_vectors(pkg, oracle, eng):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "gates_n16_seed4242.npz"))
+    ks = oracle.keygen(ob.params_default(int(g["n"])), seed=int(g["seed"]))
+    key = eng.cloud_key_from_arrays(pkg.Params.default(int(g["n"])), ks.bk_coef(), ks.ksk())
+    a, b, c = (np.ascontiguousarray(g[k]) for k in ("a", "b", "c"))
+    for op in BIN_OPS + ["MUX"]:
+        got = eng.gate_batch(key, op, a, b, c if op == "MUX" else None)
+        want = np.ascontiguousarray(g["out_" + op])
+        assert (ks.decrypt(got) == ks.decrypt(want)).all(), op
+        assert torus_dist(ks.phase(got), ks.phase(want)).max() < PHASE_TOL, op
+    key.close(); ks.free()
+
+
+def test_stage_parity(eng, full):
+    """blind rotation + extraction against the oracle (phase tolerance), key switch bit-exact"""
+    ks, key = full
+    a, b = ks.encrypt([1, 0, 1, 1, 0, 1, 0, 0], 1), ks.encrypt([1, 1, 0, 1, 0, 0, 1, 0], 2)
+    x = (a + b).astype(np.int32)
+    x[:, 630] -= 1 << 29
+    ext_gpu = eng.bootstrap_woks(key, x)
+    ext_cpu = ks.bootstrap_woks(x)
+    assert torus_dist(ks.phase_extracted(ext_gpu), ks.phase_extracted(ext_cpu)).max() < 1 << 12
+    assert torus_dist(ext_gpu, ext_cpu).max() < 1 << 12      # coefficient-wise, ~2^-20 of the torus
+    assert (eng.keyswitch(key, ext_cpu) == ks.keyswitch(ext_cpu)).all()  # integer path: bit-exact
+
+
+def test_aliasing_and_empty(eng, full):
+    ks, key = full
+    a, b = ks.encrypt([1, 1, 0], 1), ks.encrypt([1, 0, 0], 2)
+    out = eng.gate_batch(key, "AND", a, b)
+    assert list(ks.decrypt(out)) == [1, 0, 0]
+    assert eng.gate_batch(key, "AND", a[:0], b[:0]).shape == (0, 631)
+    # ragged batch sizes around the CTA packing (2 gates per CTA) and one above a wave
+    for count in (1, 3, 5, 593):
+        bits = np.arange(count) % 2
+        x = ks.encrypt(bits, 50 + count)
+        y = ks.encrypt(1 - bits, 60 + count)
+        assert (ks.decrypt(eng.gate_batch(key, "OR", x, y)) == 1).all()
+        assert (ks.decrypt(eng.gate_batch(key, "XOR", x, x.copy())) == 0).all()
+
+
+def test_large_batch_truth_table(pkg, eng):
+    """2^15 independent NANDs on GPU-generated key and ciphertexts (BASELINE.json config 2, scaled):
+    every decrypted result must equal the truth table, and the phases must sit at +-1/8."""
+    p = pkg.Params.default(630)
+    sk, key = eng.keygen(p, seed=314_1592_657)
+    count = 1 << 15
+    rng = np.random.default_rng(5)
+    ba, bb = rng.integers(0, 2, count).astype(np.int32), rng.integers(0, 2, count).astype(np.int32)
+    da, db, do = (eng.device_alloc(count * 632 * 4) for _ in range(3))
+    sk.encrypt_to_device(ba, da, seed=1)
+    sk.encrypt_to_device(bb, db, seed=2)
+    assert (sk.decrypt_from_device(da, count) == ba).all()
+    eng.gate_batch_device(key, "NAND", do, da, db, count=count)
+    bits, ph = sk.decrypt_from_device(do, count, want_phases=True)
+    assert (bits == 1 - (ba & bb)).all()
+    dev = np.abs(np.abs(ph.astype(np.float64) / 2 ** 32) - 0.125)
+    assert dev.max() < 0.04 and dev.std() < 0.01
+    for ptr in (da, db, do):
+        eng.device_free(ptr)
+    key.close(); sk.close()
+
+
+def test_gpu_keygen_is_a_valid_key_for_the_oracle(pkg, oracle, eng):
+    """Keys made on the GPU (Keygen/keygen.c's role) must work in the CPU oracle and vice versa."""
+    p = pkg.Params.default(20)
+    sk, key, bk, ksk = eng.keygen(p, seed=77, export=True)
+    lwe, tlwe = sk.export()
+    ks = oracle.from_arrays(ob.params_default(20), lwe, tlwe, bk, ksk)
+    a, b = ks.encrypt([0, 0, 1, 1], 1), ks.encrypt([0, 1, 0, 1], 2)
+    want = ks.gate_batch(ob.OPS["NAND"], a, b)
+    assert list(ks.decrypt(want)) == [1, 1, 1, 0]
+    got = eng.gate_batch(key, "NAND", a, b)
+    assert list(ks.decrypt(got)) == [1, 1, 1, 0]
+    assert torus_dist(ks.phase(got), ks.phase(want)).max() < PHASE_TOL
+    key.close(); sk.close(); ks.free()
+
+
+# ------------------------------------------------------------------ circuits
+def _inputs(ks, words, seed):
+    return np.concatenate([ks.encrypt_word(w, seed + i) for i, w in enumerate(words)])
+
+
+def _chunks(v, nc):
+    return [(v >> (32 * i)) & 0xFFFFFFFF for i in range(nc)]
+
+
+def _decode(ks, out, nwords):
+    return sum(ks.decrypt_word(out[32 * i:32 * (i + 1)]) << (32 * i) for i in range(nwords))
+
+
+@pytest.mark.parametrize("kind,width", [(1, 32), (1, 64), (1, 256), (2, 32), (2, 128), (4, 32), (5, 32)])
+def test_circuits_default_params_vs_integers(pkg, eng, full, kind, width):
+    ks, key = full
+    nc = width // 32
+    circ = eng.circuit(kind, width)
+    rng = np.random.default_rng(kind * 1000 + width)
+    n_expr = 3 if kind in (1, 2) else 2
+    ins, expect = [], []
+    for e in range(n_expr):
+        a = int(rng.integers(0, 2 ** 62)) ** 5 % (1 << width)
+        b = int(rng.integers(0, 2 ** 62)) ** 5 % (1 << width)
+        if e == 0 and kind in (1, 4):
+            a = b = 1 << (width - 2)          # Client1/process.c:94-99 stock operand 2^(bits-2)
+        if kind == 5:
+            c = int(rng.integers(0, 2 ** 31))
+            ins.append(_inputs(ks, [a, b, c, 0, 0], 100 * e))
+            expect.append((a * b + c) % (1 << 64))
+        else:
+            ins.append(_inputs(ks, _chunks(a, nc) + _chunks(b, nc) + [0], 100 * e))
+            expect.append({1: (a + b) % (1 << width), 2: (a - b) % (1 << width), 4: a * b}[kind])
+    out = eng.eval(key, circ, np.ascontiguousarray(np.stack(ins)))
+    for e in range(n_expr):
+        assert _decode(ks, out[e], circ.n_outputs // 32) == expect[e], (kind, width, e)
+
+
+@pytest.mark.parametrize("width", [64, 128])
+def test_wide_multipliers_small_params(pkg, eng, small, width):
+    ks, _, key = small
+    nc = width // 32
+    circ = eng.circuit(4, width)
+    rng = np.random.default_rng(width)
+    a = int.from_bytes(rng.bytes(width // 8), "little")
+    b = int.from_bytes(rng.bytes(width // 8), "little")
+    ins = _inputs(ks, _chunks(a, nc) + _chunks(b, nc) + [0], 7)[None]
+    out = eng.eval(key, circ, np.ascontiguousarray(ins))
+    assert _decode(ks, out[0], 2 * nc) == a * b
+
+
+def test_mul32_matches_oracle_circuit(eng, small):
+    """the same mul32 on the oracle (11 264 gate calls, in cloud.c's order) and on the GPU (255 levels)"""
+    ks, _, key = small
+    a, b = 0x9E3779B9, 0x7F4A7C15
+    A, B, C = ks.encrypt_word(a, 1), ks.encrypt_word(b, 2), ks.encrypt_word(0, 3)
+    hi, lo = ks.mul32(A, B, C)
+    circ = eng.circuit(4, 32)
+    out = eng.eval(key, circ, np.ascontiguousarray(np.concatenate([A, B, C])[None]))[0]
+    assert (ks.decrypt(out[:32]) == ks.decrypt(lo)).all() and (ks.decrypt(out[32:]) == ks.decrypt(hi)).all()
+    assert _decode(ks, out, 2) == a * b
+    assert torus_dist(ks.phase(out[:32]), ks.phase(lo)).max() < PHASE_TOL
+
+
+# ------------------------------------------------------------------ the ./cloud process contract
+CLOUD_CASES = [(1, 0, 0, 32, 1 << 30, 1 << 30), (1, 2, 2, 32, 5, 7), (2, 0, 2, 32, 100, 23), (2, 0, 0, 32, 1000, 1),
+               (2, 0, 0, 32, 1, 1000), (1, 2, 0, 32, 50, 20), (2, 2, 2, 32, 3, 10), (1, 0, 0, 64, (1 << 62) + 12345, (1 << 62) + 1),
+               (4, 2, 0, 32, 77777, 99999), (4, 0, 0, 64, (1 << 62), (1 << 62))]
+
+
+@pytest.mark.parametrize("op,s1,s2,width,a,b", CLOUD_CASES)
+def test_cloud_run_files(tmp_path, oracle, eng, small, op, s1, s2, width, a, b):
+    """keygen -> alice -> [GPU cloud] -> verif through the reference's files: cloud.key, nbit.key,
+    cloud.data, operator.txt in; answer.data out (Cloud/cloud.c:656-916), against the oracle's
+    cloud main() on the same files and against Python integers."""
+    ks, nbit, _ = small
+    d = str(tmp_path)
+    ks.write_cloud_key(os.path.join(d, "cloud.key"))
+    nbit.write_secret_key(os.path.join(d, "nbit.key"))
+    data = np.concatenate([oracle.alice(ks, nbit, s1, width, a, seed=1), oracle.alice(ks, nbit, s2, width, b, seed=2)])
+    ks.write_samples(data, os.path.join(d, "cloud.data"))
+    open(os.path.join(d, "operator.txt"), "w").write(str(op))
+    rc, secs = eng.cloud_run(d)
+    assert rc == 0
+    rec = 4 + 4 * 9 + 8
+    assert os.path.getsize(os.path.join(d, "answer.data")) == 352 * rec
+    ans = ks.read_samples(os.path.join(d, "answer.data"), 352)
+    code, w, chunks = oracle.verif(ks, nbit, ans)
+    rc_o, ans_o = oracle.cloud_main(ks, nbit, op, data)
+    assert (code, w, chunks) == oracle.verif(ks, nbit, ans_o)          # decrypt-identical to the reference flow
+    va, vb = (-a if s1 == 2 else a), (-b if s2 == 2 else b)
+    assert ob.decode_result(op, code, w, chunks) == {1: va + vb, 2: va - vb, 4: va * vb}[op]
+    # padding blocks are copies of operand 1's carry block (cloud.c:901-916)
+    nres = (2 * width if op == 4 else width) // 32
+    assert (ans[(2 + nres) * 32:(3 + nres) * 32] == data[320:352]).all() and (ans[320:352] == data[320:352]).all()
+    if op == 4:
+        assert os.path.exists(os.path.join(d, "averagestandard.txt"))
+
+
+def test_cloud_run_abort_path(tmp_path, oracle, eng, small):
+    ks, nbit, _ = small
+    d = str(tmp_path)
+    ks.write_cloud_key(os.path.join(d, "cloud.key"))
+    nbit.write_secret_key(os.path.join(d, "nbit.key"))
+    data = np.concatenate([oracle.alice(ks, nbit, 0, 256, 3, seed=1), oracle.alice(ks, nbit, 0, 256, 5, seed=2)])
+    ks.write_samples(data, os.path.join(d, "cloud.data"))
+    open(os.path.join(d, "operator.txt"), "w").write("4")
+    rc, _ = eng.cloud_run(d)
+    assert rc == 126                                                    # Cloud/cloud.c:860-864
+    assert os.path.getsize(os.path.join(d, "answer.data")) == 64 * (4 + 4 * 9 + 8)
+
+
+def test_cloud_executable_and_libtfhe_api(tmp_path, oracle, small):
+    """(1) the drop-in ./cloud binary; (2) a C++ program written against include/tfhe/tfhe.h exactly like
+    Cloud/cloud.c's add() (pointer arithmetic on LweSample arrays, aliasing result/input) linked
+    against libieache_b200.so instead of libtfhe."""
+    ks, nbit, _ = small
+    d = str(tmp_path)
+    ks.write_cloud_key(os.path.join(d, "cloud.key"))
+    ks.write_secret_key(os.path.join(d, "secret.key"))
+    nbit.write_secret_key(os.path.join(d, "nbit.key"))
+    a, b = 123456789, 987654321
+    data = np.concatenate([oracle.alice(ks, nbit, 0, 32, a, seed=1), oracle.alice(ks, nbit, 0, 32, b, seed=2)])
+    ks.write_samples(data, os.path.join(d, "cloud.data"))
+    open(os.path.join(d, "operator.txt"), "w").write("1")
+    r = subprocess.run([os.path.join(ROOT, "ie-ache_b200", "cloud")], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    assert "Computation Time:" in r.stdout
+    code, w, chunks = oracle.verif(ks, nbit, ks.read_samples(os.path.join(d, "answer.data"), 352))
+    assert (code, w, chunks[0]) == (0, 32, a + b)
+    # (2)
+    src = os.path.join(ROOT, "tests", "compat", "add_like_cloud.cpp")
+    exe = os.path.join(d, "add_like_cloud")
+    cc = subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+                         "-L", os.path.join(ROOT, "ie-ache_b200"), "-lieache_b200", "-Wl,-rpath," + os.path.join(ROOT, "ie-ache_b200")],
+                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert cc.returncode == 0, cc.stdout
+    r = subprocess.run([exe], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    assert f"sum={a + b}" in r.stdout and "mux_ok=1" in r.stdout, r.stdout
