@@ -94,6 +94,11 @@ def lib() -> ctypes.CDLL:
     L.ieache_circuit_eval.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]
     L.ieache_circuit_eval_device.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]
     L.ieache_cloud_run.argtypes = [c_void_p, c_char_p, POINTER(c_double)]
+    L.ieache_ctx_timer_start.argtypes = [c_void_p]
+    L.ieache_ctx_timer_stop.argtypes = [c_void_p, POINTER(c_double)]
+    L.ieache_measure_fp64_peak.argtypes = [c_void_p, POINTER(c_double)]
+    L.ieache_host_alloc.argtypes = [c_size_t, POINTER(c_void_p)]
+    L.ieache_host_free.argtypes = [c_void_p]
     L.ieache_keygen.argtypes = [c_void_p, POINTER(Params), c_uint64, POINTER(c_void_p), POINTER(c_void_p), c_void_p, c_void_p]
     L.ieache_secretkey_import.argtypes = [c_void_p, POINTER(Params), c_void_p, c_void_p, POINTER(c_void_p)]
     L.ieache_secretkey_export.argtypes = [c_void_p, c_void_p, c_void_p]
@@ -153,6 +158,18 @@ class CloudKey:
         if self._h:
             lib().ieache_cloudkey_destroy(self._h)
             self._h = None
+
+
+def pinned_array(shape, dtype=np.int32) -> np.ndarray:
+    """numpy view of page-locked host memory (cudaHostAlloc); freed when the array is collected."""
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = c_void_p()
+    _check(lib().ieache_host_alloc(max(nbytes, 1), byref(p)))
+    buf = (ctypes.c_byte * nbytes).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    import weakref
+    weakref.finalize(buf, lib().ieache_host_free, p)
+    return arr
 
 
 class SecretKey:
@@ -309,6 +326,19 @@ class Engine:
         br, ks, nbr, nks = c_double(), c_double(), c_uint64(), c_uint64()
         _check(lib().ieache_ctx_kernel_times(self._h, byref(br), byref(ks), byref(nbr), byref(nks), int(reset)))
         return {"blind_rotate_ms": br.value, "keyswitch_ms": ks.value, "blind_rotate_launches": nbr.value, "keyswitch_launches": nks.value}
+
+    def timer_start(self):
+        _check(lib().ieache_ctx_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = c_double()
+        _check(lib().ieache_ctx_timer_stop(self._h, byref(ms)))
+        return ms.value
+
+    def fp64_peak_tflops(self) -> float:
+        t = c_double()
+        _check(lib().ieache_measure_fp64_peak(self._h, byref(t)))
+        return t.value
 
     @property
     def launch_count(self) -> int:

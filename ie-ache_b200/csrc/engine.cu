@@ -11,6 +11,7 @@
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -50,11 +51,18 @@ struct TimedLaunch { cudaEvent_t a, b; int kind; };
 struct ieache_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t ks_stream = nullptr;   /* key switches of chunk c overlap the blind rotation of chunk c+1 */
+    cudaEvent_t ev_br[2] = {nullptr, nullptr}, ev_ks[2] = {nullptr, nullptr};
+    /* measured on B200 (profiles/README.md): running the key switch under the next blind rotation is
+     * SLOWER (92k vs 98k gates/s) — its gather stream evicts the bootstrapping key from L2 and its CTAs
+     * displace blind-rotation CTAs — so the overlap is off unless IEACHE_OVERLAP_KS=1 */
+    bool overlap_ks = false;
     uint64_t launches = 0;
     int32_t *d_ext = nullptr; size_t ext_cap = 0;      /* extracted samples scratch */
     int32_t *d_stage[4] = {nullptr, nullptr, nullptr, nullptr}; size_t stage_cap[4] = {0, 0, 0, 0};
     int32_t *d_wires = nullptr; size_t wires_cap = 0;
     bool timing = false;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
     std::vector<TimedLaunch> timed;
     double br_ms = 0, ks_ms = 0; uint64_t br_n = 0, ks_n = 0;
 };
@@ -62,7 +70,7 @@ struct ieache_ctx {
 static int ensure(ieache_ctx *ctx, int32_t **buf, size_t *cap, size_t words)
 {
     if (*cap >= words) return IEACHE_OK;
-    if (*buf) { cudaStreamSynchronize(ctx->stream); cudaFree(*buf); *buf = nullptr; *cap = 0; }
+    if (*buf) { cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->ks_stream); cudaFree(*buf); *buf = nullptr; *cap = 0; }
     CU(cudaMalloc((void **)buf, words * sizeof(int32_t)));
     *cap = words;
     return IEACHE_OK;
@@ -81,7 +89,16 @@ extern "C" int ieache_ctx_create(int device, ieache_ctx **out)
     std::unique_ptr<ieache_ctx> ctx(new ieache_ctx());
     ctx->device = device;
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CU(cudaStreamCreateWithPriority(&ctx->ks_stream, cudaStreamNonBlocking, prio_hi));
+    for (int i = 0; i < 2; i++) {
+        CU(cudaEventCreateWithFlags(&ctx->ev_br[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_ks[i], cudaEventDisableTiming));
+    }
     CU(upload_twiddles());
+    const char *ov = getenv("IEACHE_OVERLAP_KS");
+    ctx->overlap_ks = ov && atoi(ov) != 0;
     *out = ctx.release();
     return IEACHE_OK;
 }
@@ -94,6 +111,9 @@ extern "C" void ieache_ctx_destroy(ieache_ctx *ctx)
     cudaFree(ctx->d_ext);
     for (int i = 0; i < 4; i++) cudaFree(ctx->d_stage[i]);
     cudaFree(ctx->d_wires);
+    cudaStreamSynchronize(ctx->ks_stream);
+    for (int i = 0; i < 2; i++) { cudaEventDestroy(ctx->ev_br[i]); cudaEventDestroy(ctx->ev_ks[i]); }
+    cudaStreamDestroy(ctx->ks_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -101,6 +121,7 @@ extern "C" int ieache_ctx_sync(ieache_ctx *ctx)
 {
     if (!ctx) return fail(IEACHE_ERR_ARG, "null ctx");
     CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->ks_stream));
     return IEACHE_OK;
 }
 extern "C" uint64_t ieache_ctx_launch_count(const ieache_ctx *ctx) { return ctx ? ctx->launches : 0; }
@@ -113,6 +134,7 @@ extern "C" int ieache_ctx_set_timing(ieache_ctx *ctx, int enabled)
 static int drain_timed(ieache_ctx *ctx)
 {
     CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->ks_stream));
     for (auto &t : ctx->timed) {
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, t.a, t.b));
@@ -132,6 +154,47 @@ extern "C" int ieache_ctx_kernel_times(ieache_ctx *ctx, double *br_ms, double *k
     if (br_n) *br_n = ctx->br_n;
     if (ks_n) *ks_n = ctx->ks_n;
     if (reset) { ctx->br_ms = ctx->ks_ms = 0; ctx->br_n = ctx->ks_n = 0; }
+    return IEACHE_OK;
+}
+
+extern "C" int ieache_ctx_timer_start(ieache_ctx *ctx)
+{
+    if (!ctx) return fail(IEACHE_ERR_ARG, "null ctx");
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->t0) { CU(cudaEventCreate(&ctx->t0)); CU(cudaEventCreate(&ctx->t1)); }
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaEventRecord(ctx->t0, ctx->stream));
+    return IEACHE_OK;
+}
+extern "C" int ieache_ctx_timer_stop(ieache_ctx *ctx, double *elapsed_ms)
+{
+    if (!ctx || !ctx->t0 || !elapsed_ms) return fail(IEACHE_ERR_ARG, "timer not started");
+    CU(cudaEventRecord(ctx->t1, ctx->stream));
+    CU(cudaEventSynchronize(ctx->t1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ctx->t0, ctx->t1));
+    *elapsed_ms = ms;
+    return IEACHE_OK;
+}
+extern "C" int ieache_measure_fp64_peak(ieache_ctx *ctx, double *tflops)
+{
+    if (!ctx || !tflops) return fail(IEACHE_ERR_ARG, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    double best = 0;
+    CU(launch_fp64_peak(ctx->stream, &best));
+    ctx->launches += 4;
+    *tflops = best;
+    return IEACHE_OK;
+}
+extern "C" int ieache_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return fail(IEACHE_ERR_ARG, "null out");
+    CU(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return IEACHE_OK;
+}
+extern "C" int ieache_host_free(void *ptr)
+{
+    CU(cudaFreeHost(ptr));
     return IEACHE_OK;
 }
 
@@ -357,21 +420,24 @@ extern "C" int ieache_sym_decrypt_device(ieache_ctx *ctx, const ieache_secretkey
 }
 
 /* ------------------------------------------------------------------ launches with optional timing */
-static int run_br(ieache_ctx *ctx, const ieache_cloudkey *key, const GateAddr &ga, const int32_t *A, const int32_t *B, int ext_base)
+static int run_br(ieache_ctx *ctx, const ieache_cloudkey *key, const GateAddr &ga, const int32_t *A, const int32_t *B, int ext_base,
+                  int32_t *ext = nullptr)
 {
     TimedLaunch t{};
     if (ctx->timing) { CU(cudaEventCreate(&t.a)); CU(cudaEventCreate(&t.b)); t.kind = 0; CU(cudaEventRecord(t.a, ctx->stream)); }
-    CU(launch_blind_rotate(key->dp, key->bkfft, ga, A, B, ctx->d_ext, ext_base, ctx->stream));
+    CU(launch_blind_rotate(key->dp, key->bkfft, ga, A, B, ext ? ext : ctx->d_ext, ext_base, ctx->stream));
     if (ctx->timing) { CU(cudaEventRecord(t.b, ctx->stream)); ctx->timed.push_back(t); }
     ctx->launches++;
     return IEACHE_OK;
 }
-static int run_ks(ieache_ctx *ctx, const ieache_cloudkey *key, const GateAddr &ga, int32_t *out, int pair_offset, int32_t cst_post)
+static int run_ks(ieache_ctx *ctx, const ieache_cloudkey *key, const GateAddr &ga, int32_t *out, int pair_offset, int32_t cst_post,
+                  const int32_t *ext = nullptr, cudaStream_t st = nullptr)
 {
     TimedLaunch t{};
-    if (ctx->timing) { CU(cudaEventCreate(&t.a)); CU(cudaEventCreate(&t.b)); t.kind = 1; CU(cudaEventRecord(t.a, ctx->stream)); }
-    CU(launch_keyswitch(key->dp, key->ksk, ga, out, ctx->d_ext, pair_offset, cst_post, ctx->stream));
-    if (ctx->timing) { CU(cudaEventRecord(t.b, ctx->stream)); ctx->timed.push_back(t); }
+    if (!st) st = ctx->stream;
+    if (ctx->timing) { CU(cudaEventCreate(&t.a)); CU(cudaEventCreate(&t.b)); t.kind = 1; CU(cudaEventRecord(t.a, st)); }
+    CU(launch_keyswitch(key->dp, key->ksk, ga, out, ext ? ext : ctx->d_ext, pair_offset, cst_post, st));
+    if (ctx->timing) { CU(cudaEventRecord(t.b, st)); ctx->timed.push_back(t); }
     ctx->launches++;
     if (ctx->timed.size() > 4096) return drain_timed(ctx);
     return IEACHE_OK;
@@ -380,7 +446,7 @@ static int run_ks(ieache_ctx *ctx, const ieache_cloudkey *key, const GateAddr &g
 /* ------------------------------------------------------------------ batched gates */
 static const int8_t k_lin[10][3] = {{+1, -1, -1}, {+1, +1, +1}, {-1, +1, +1}, {+2, +2, +2}, {-2, -2, -2},
                                     {-1, -1, -1}, {-1, -1, +1}, {-1, +1, -1}, {+1, -1, +1}, {+1, +1, -1}};
-constexpr size_t kChunk = 1u << 16; /* gates per launch: bounds the extracted-sample scratch to 2 x 270 MB */
+constexpr size_t kChunk = 1u << 16; /* gates per launch: bounds the extracted-sample scratch to 2 x 135 MB (x2 for MUX) */
 
 extern "C" int ieache_gate_batch_device(ieache_ctx *ctx, const ieache_cloudkey *key, int op, int32_t *out, const int32_t *a,
                                         const int32_t *b, const int32_t *c, int32_t imm, size_t count)
@@ -399,11 +465,18 @@ extern "C" int ieache_gate_batch_device(ieache_ctx *ctx, const ieache_cloudkey *
     }
     if (op < 0 || op > IEACHE_OP_MUX) return fail(IEACHE_ERR_ARG, "unknown op %d", op);
     if (!b || (op == IEACHE_OP_MUX && !c)) return fail(IEACHE_ERR_ARG, "null input operand");
+    /* chunks of <= 32768 gates, double-buffered extracted samples: the (memory-bound) key switch of
+     * chunk c runs on a second, higher-priority stream under the (FP64-bound) blind rotation of c+1 */
     const size_t per = std::min(count, kChunk);
-    int rc = ensure(ctx, &ctx->d_ext, &ctx->ext_cap, per * kExtStride * (op == IEACHE_OP_MUX ? 2 : 1));
+    const size_t slot_words = per * kExtStride * (op == IEACHE_OP_MUX ? 2 : 1);
+    int rc = ensure(ctx, &ctx->d_ext, &ctx->ext_cap, 2 * slot_words);
     if (rc) return rc;
-    for (size_t off = 0; off < count; off += per) {
+    size_t chunk = 0;
+    for (size_t off = 0; off < count; off += per, chunk++) {
         const size_t m = std::min(per, count - off);
+        const int slot = (int)(chunk & 1);
+        int32_t *ext = ctx->d_ext + slot * slot_words;
+        if (chunk >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_ks[slot], 0));
         GateAddr ga{};
         ga.tmpl = nullptr; ga.ntempl = (int)m; ga.n_inst = 1; ga.inst_samples = 0; ga.stride = kLweStride;
         const int32_t *pa = a + off * kLweStride, *pb = b + off * kLweStride;
@@ -412,16 +485,22 @@ extern "C" int ieache_gate_batch_device(ieache_ctx *ctx, const ieache_cloudkey *
             /* bootsMUX: u1 = BR((0,-mu)+a+b), u2 = BR((0,-mu)-a+c), out = KS((0,mu)+u1+u2) */
             const int32_t *pc = c + off * kLweStride;
             ga.uni = GateT{0, 0, 0, +1, +1, -1};
-            if ((rc = run_br(ctx, key, ga, pa, pb, 0))) return rc;
+            if ((rc = run_br(ctx, key, ga, pa, pb, 0, ext))) return rc;
             ga.uni = GateT{0, 0, 0, -1, +1, -1};
-            if ((rc = run_br(ctx, key, ga, pa, pc, (int)m))) return rc;
-            if ((rc = run_ks(ctx, key, ga, po, (int)m, mu))) return rc;
+            if ((rc = run_br(ctx, key, ga, pa, pc, (int)m, ext))) return rc;
         } else {
             ga.uni = GateT{0, 0, 0, k_lin[op][1], k_lin[op][2], k_lin[op][0]};
-            if ((rc = run_br(ctx, key, ga, pa, pb, 0))) return rc;
-            if ((rc = run_ks(ctx, key, ga, po, 0, 0))) return rc;
+            if ((rc = run_br(ctx, key, ga, pa, pb, 0, ext))) return rc;
         }
+        cudaStream_t kst = ctx->overlap_ks ? ctx->ks_stream : ctx->stream;
+        CU(cudaEventRecord(ctx->ev_br[slot], ctx->stream));
+        if (ctx->overlap_ks) CU(cudaStreamWaitEvent(kst, ctx->ev_br[slot], 0));
+        if ((rc = run_ks(ctx, key, ga, po, op == IEACHE_OP_MUX ? (int)m : 0, op == IEACHE_OP_MUX ? mu : 0, ext, kst))) return rc;
+        CU(cudaEventRecord(ctx->ev_ks[slot], kst));
     }
+    /* join: later work on the context stream sees every key switch */
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_ks[0], 0));
+    if (chunk >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_ks[1], 0));
     return IEACHE_OK;
 }
 

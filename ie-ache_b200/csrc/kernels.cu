@@ -19,6 +19,7 @@
 #include "br_core.h"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace ieache {
 
@@ -105,8 +106,11 @@ constexpr int kBufBytes = kBufElems * 16;
 constexpr int kAbarBytes = 2080;
 constexpr int kGroupSmem = kAccBytes + 2 * kBufBytes + kAbarBytes; /* 28704 */
 
-template <int L, int G>
-__global__ void __launch_bounds__(64 * G)
+/* L = gadget length, G = gates (64-thread groups) per CTA, MINB = CTAs per SM the register
+ * allocation is tuned for, ROLL = keep the (k+1)l forward transforms in a rolled loop so the
+ * step body fits the 32 KB instruction cache (the fully unrolled body is ~60 KB of SASS) */
+template <int L, int G, int MINB, bool ROLL, bool NOBK = false>
+__global__ void __launch_bounds__(64 * G, MINB)
 blind_rotate_kernel(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
                     const int32_t *__restrict__ baseB, int32_t *__restrict__ ext)
 {
@@ -170,18 +174,16 @@ blind_rotate_kernel(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga,
     for (int i = 0; i < n; i++) {
         const int a = abar[i];
         if (a == 0) continue; /* uniform inside the group */
-        double sr[2][8], si[2][8];
+        double s0r[8], s0i[8], s1r[8], s1i[8];
 #pragma unroll
-        for (int j = 0; j < 2; j++)
-#pragma unroll
-            for (int r = 0; r < 8; r++) { sr[j][r] = 0.0; si[j][r] = 0.0; }
-        const double2 *bk_i = bkfft + (size_t)i * kBkStride + tid;
+        for (int r = 0; r < 8; r++) { s0r[r] = 0.0; s0i[r] = 0.0; s1r[r] = 0.0; s1i[r] = 0.0; }
+        const double2 *bk_r = bkfft + (size_t)i * kBkStride + tid;
 
-#pragma unroll
+#pragma unroll(ROLL ? 1 : 2)
         for (int q = 0; q < 2; q++) {
             int32_t c[16];
             rot_minus_one(acc + q * kN, tid, a, c);
-#pragma unroll
+#pragma unroll(ROLL ? 1 : L)
             for (int pp = 0; pp < L; pp++) {
                 const int shift = 32 - (pp + 1) * Bgbit;
                 double xr[8], xi[8];
@@ -193,28 +195,30 @@ blind_rotate_kernel(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga,
                 cd *buf = toggle ? bufB : bufA;
                 toggle ^= 1;
                 fwd_transform(xr, xi, buf, tid, grp, w1, w2, w3);
-                const double2 *bk_r = bk_i + (size_t)(q * L + pp) * kRowElems;
 #pragma unroll
-                for (int j = 0; j < 2; j++)
-#pragma unroll
-                    for (int r = 0; r < 8; r++) {
-                        const double2 b = __ldg(bk_r + j * kHalfN + r * 64);
-                        cmac(sr[j][r], si[j][r], xr[r], xi[r], b.x, b.y);
-                    }
+                for (int r = 0; r < 8; r++) {
+                    const double2 b0 = NOBK ? make_double2(1.0 + r, 0.5) : __ldg(bk_r + r * 64);
+                    const double2 b1 = NOBK ? make_double2(0.25, 2.0 - r) : __ldg(bk_r + kHalfN + r * 64);
+                    cmac(s0r[r], s0i[r], xr[r], xi[r], b0.x, b0.y);
+                    cmac(s1r[r], s1i[r], xr[r], xi[r], b1.x, b1.y);
+                }
+                bk_r += kRowElems;
             }
         }
-        /* inverse transforms and ACC update */
-#pragma unroll
+        /* inverse transforms and ACC update; the second pass reuses the code of the first */
+#pragma unroll(ROLL ? 1 : 2)
         for (int j = 0; j < 2; j++) {
             cd *buf = toggle ? bufB : bufA;
             toggle ^= 1;
-            inv_transform(sr[j], si[j], buf, tid, grp, w1, w2, w3);
+            inv_transform(s0r, s0i, buf, tid, grp, w1, w2, w3);
             int32_t *accj = acc + j * kN;
 #pragma unroll
             for (int m = 0; m < 8; m++) {
-                accj[tid + 64 * m] += round_to_torus(sr[j][m]);
-                accj[tid + 64 * m + 512] += round_to_torus(si[j][m]);
+                accj[tid + 64 * m] += round_to_torus(s0r[m]);
+                accj[tid + 64 * m + 512] += round_to_torus(s0i[m]);
             }
+#pragma unroll
+            for (int r = 0; r < 8; r++) { s0r[r] = s1r[r]; s0i[r] = s1i[r]; }
         }
         group_sync(grp);
     }
@@ -225,9 +229,27 @@ blind_rotate_kernel(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga,
     if (tid == 0) o[kN] = acc[kN];
 }
 
-constexpr int kGroupsPerCta = 2;
-int blind_rotate_groups_per_cta() { return kGroupsPerCta; }
+/* launch configuration: IEACHE_BR_VARIANT selects among the compiled variants (tuning aid) */
+static int br_variant()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("IEACHE_BR_VARIANT"); v = e ? atoi(e) : 7; }
+    return v;
+}
+int blind_rotate_groups_per_cta() { const int v = br_variant(); return (v == 4) ? 4 : ((v == 0 || v == 1 || v == 3 || v == 5 || v == 6) ? 2 : 1); }
 int blind_rotate_smem_bytes(int groups) { return groups * kGroupSmem; }
+
+template <int L, int G, int MINB, bool ROLL, bool NOBK = false>
+static cudaError_t launch_br_variant(const DevParams &p, const double2 *bkfft, const GateAddr &ga, const int32_t *baseA,
+                                     const int32_t *baseB, int32_t *ext, long long count, cudaStream_t s)
+{
+    const int smem = G * kGroupSmem;
+    const int grid = (int)((count + G - 1) / G);
+    cudaError_t e = cudaFuncSetAttribute(blind_rotate_kernel<L, G, MINB, ROLL, NOBK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    blind_rotate_kernel<L, G, MINB, ROLL, NOBK><<<grid, 64 * G, smem, s>>>(p, bkfft, ga, baseA, baseB, ext);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_blind_rotate(const DevParams &p, const double2 *bkfft, const GateAddr &ga, const int32_t *baseA,
                                 const int32_t *baseB, int32_t *ext, int ext_base, cudaStream_t s)
@@ -235,22 +257,25 @@ cudaError_t launch_blind_rotate(const DevParams &p, const double2 *bkfft, const 
     const long long count = (long long)ga.ntempl * ga.n_inst;
     if (count <= 0) return cudaSuccess;
     ext += (size_t)ext_base * kExtStride;
-    constexpr int G = kGroupsPerCta;
-    const int smem = G * kGroupSmem;
-    const int grid = (int)((count + G - 1) / G);
-    cudaError_t e;
-    if (p.l == 3) {
-        e = cudaFuncSetAttribute(blind_rotate_kernel<3, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        blind_rotate_kernel<3, G><<<grid, 64 * G, smem, s>>>(p, bkfft, ga, baseA, baseB, ext);
-    } else if (p.l == 2) {
-        e = cudaFuncSetAttribute(blind_rotate_kernel<2, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        blind_rotate_kernel<2, G><<<grid, 64 * G, smem, s>>>(p, bkfft, ga, baseA, baseB, ext);
-    } else {
-        return cudaErrorInvalidValue;
+    if (p.l == 2) return launch_br_variant<2, 1, 4, false>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    if (p.l != 3) return cudaErrorInvalidValue;
+    switch (br_variant()) {
+    case 0: return launch_br_variant<3, 2, 2, false>(p, bkfft, ga, baseA, baseB, ext, count, s); /* round-1 first version */
+    case 2: return launch_br_variant<3, 1, 6, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 3: return launch_br_variant<3, 2, 2, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 4: return launch_br_variant<3, 4, 1, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 5: return launch_br_variant<3, 2, 4, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 6: return launch_br_variant<3, 2, 3, false>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 8: return launch_br_variant<3, 1, 5, false>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 9: return launch_br_variant<3, 1, 6, false>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 10: return launch_br_variant<3, 1, 5, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    /* timing experiments only (wrong results): no BK loads */
+    case 107: return launch_br_variant<3, 1, 4, false, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 109: return launch_br_variant<3, 1, 6, false, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 102: return launch_br_variant<3, 1, 6, true, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 1: return launch_br_variant<3, 2, 3, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    default: return launch_br_variant<3, 1, 4, false>(p, bkfft, ga, baseA, baseB, ext, count, s); /* 7: best measured */
     }
-    return cudaGetLastError();
 }
 
 /* ------------------------------------------------------------------ key switch */
@@ -411,6 +436,52 @@ cudaError_t launch_circuit_gather_outputs(int32_t *outputs, const int32_t *wires
     (void)n;
     const long long blocks = (long long)n_expr * n_outputs;
     circuit_gather_kernel<<<(unsigned)blocks, 160, 0, s>>>(outputs, wires, out_slots, n_expr, n_outputs, n_slots);
+    return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------ FP64 pipe peak (roofline denominator) */
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters)
+{
+    double a[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+    const double m = 1.0000001, c = 1e-7;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) a[i] = fma(a[i], m, c);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += a[i];
+    if (s == 12345.678) out[0] = s; /* keep the chain alive */
+}
+cudaError_t launch_fp64_peak(cudaStream_t s, double *tflops)
+{
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    double *d = nullptr;
+    cudaError_t e = cudaMalloc((void **)&d, 8);
+    if (e != cudaSuccess) return e;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    const int iters = 4096, blocks = sms * 8, threads = 256;
+    double best = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(a, s);
+        fp64_peak_kernel<<<blocks, threads, 0, s>>>(d, iters);
+        cudaEventRecord(b, s);
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        const double flops = 2.0 * 64.0 * iters * (double)blocks * threads;
+        if (rep > 0) best = fmax(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(d);
+    *tflops = best;
     return cudaGetLastError();
 }
 

@@ -73,6 +73,9 @@ cudaError_t launch_circuit_scatter_inputs(int32_t *wires, const int32_t *inputs,
 cudaError_t launch_circuit_gather_outputs(int32_t *outputs, const int32_t *wires, const int32_t *out_slots, int n_expr,
                                           int n_outputs, int n_slots, int n, cudaStream_t s);
 
+/* dense FP64 FMA microbenchmark (best of 3), TFLOP/s */
+cudaError_t launch_fp64_peak(cudaStream_t s, double *tflops);
+
 int blind_rotate_smem_bytes(int groups);
 int blind_rotate_groups_per_cta();
 

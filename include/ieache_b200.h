@@ -66,6 +66,16 @@ int ieache_ctx_kernel_times(ieache_ctx *ctx, double *blind_rotate_ms, double *ke
                             uint64_t *blind_rotate_launches, uint64_t *keyswitch_launches, int reset);
 int ieache_ctx_set_timing(ieache_ctx *ctx, int enabled);
 
+/* step timer: CUDA events on the engine's stream (torch events only see torch's stream) */
+int ieache_ctx_timer_start(ieache_ctx *ctx);
+int ieache_ctx_timer_stop(ieache_ctx *ctx, double *elapsed_ms); /* records, synchronises, returns the elapsed device time */
+/* dense FP64 FMA throughput of this GPU (TFLOP/s, 2 flops per FMA), measured live: the roofline
+ * denominator of the transform + multiply-accumulate work (MEASURED_PEAKS.json has no FP64 figure) */
+int ieache_measure_fp64_peak(ieache_ctx *ctx, double *tflops);
+/* pinned host memory for the end-to-end path */
+int ieache_host_alloc(size_t bytes, void **out);
+int ieache_host_free(void *ptr);
+
 /* ---- cloud key: replaces new_tfheGateBootstrappingCloudKeySet_fromFile (Cloud/cloud.c:656-658) ---- */
 /* bk:  int32 [n][(k+1)l][k+1][N]  coefficient-domain TGSW samples (libtfhe bk->bk[i].all_sample[r].a[j])
  * ksk: int32 [kN][t][2^basebit][n+1]  key-switch samples (libtfhe bk->ks->ks[i][j][d])
