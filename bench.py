@@ -90,7 +90,8 @@ def cpu_port_rate(seconds_budget: float, threads: int = 0):
     """Oracle (CPU restatement of libtfhe) on `threads` host threads over independent NAND gates."""
     import oracle_bind as ob
     orc = ob.Oracle()
-    threads = threads or orc.max_threads()
+    # torchrun exports OMP_NUM_THREADS=1; the baseline must still use every host core it may run on
+    threads = threads or max(orc.max_threads(), len(os.sched_getaffinity(0)))
     ks = orc.keygen(ob.params_default(N_LWE), seed=2024)
     batch = max(threads * 2, 8)
     rng = np.random.default_rng(3)
@@ -187,7 +188,8 @@ def main():
         t_bcast_ms = 1e3 * (time.perf_counter() - tb)
         if rank != 0:
             both = kt.cpu().numpy()
-            sk = eng.secret_key_import(params, both[:N_LWE], both[N_LWE:])
+            lwe, tlwe = both[:N_LWE].copy(), both[N_LWE:].copy()
+            sk = eng.secret_key_import(params, lwe, tlwe)
 
     # ---- synthetic ciphertexts, made on the GPU (Client/alice.c's role): 2 x count samples, resident in HBM
     rng = np.random.default_rng(1000 + rank)
