@@ -94,6 +94,8 @@ def lib() -> ctypes.CDLL:
     L.ieache_circuit_eval.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]
     L.ieache_circuit_eval_device.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]
     L.ieache_cloud_run.argtypes = [c_void_p, c_char_p, POINTER(c_double)]
+    L.ieache_set_wide_max.restype = ctypes.c_int64
+    L.ieache_set_wide_max.argtypes = [ctypes.c_int64]
     L.ieache_ctx_timer_start.argtypes = [c_void_p]
     L.ieache_ctx_timer_stop.argtypes = [c_void_p, POINTER(c_double)]
     L.ieache_measure_fp64_peak.argtypes = [c_void_p, POINTER(c_double)]
@@ -107,6 +109,11 @@ def lib() -> ctypes.CDLL:
     L.ieache_sym_decrypt_device.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]
     _lib = L
     return L
+
+
+def set_wide_max(max_gates: int) -> int:
+    """Launches of <= max_gates gates use the latency kernel; returns the previous threshold."""
+    return lib().ieache_set_wide_max(max_gates)
 
 
 def _check(rc: int) -> None:

@@ -157,6 +157,12 @@ extern "C" int ieache_ctx_kernel_times(ieache_ctx *ctx, double *br_ms, double *k
     return IEACHE_OK;
 }
 
+extern "C" int64_t ieache_set_wide_max(int64_t max_gates)
+{
+    const long long old = get_wide_max();
+    if (max_gates >= 0) set_wide_max(max_gates);
+    return old;
+}
 extern "C" int ieache_ctx_timer_start(ieache_ctx *ctx)
 {
     if (!ctx) return fail(IEACHE_ERR_ARG, "null ctx");

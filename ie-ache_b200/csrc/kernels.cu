@@ -18,6 +18,7 @@
 #include "kernels.h"
 #include "br_core.h"
 
+#include <cooperative_groups.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -109,15 +110,17 @@ constexpr int kGroupSmem = kAccBytes + 2 * kBufBytes + kAbarBytes; /* 28704 */
 /* L = gadget length, G = gates (64-thread groups) per CTA, MINB = CTAs per SM the register
  * allocation is tuned for, ROLL = keep the (k+1)l forward transforms in a rolled loop so the
  * step body fits the 32 KB instruction cache (the fully unrolled body is ~60 KB of SASS) */
-template <int L, int G, int MINB, bool ROLL, bool NOBK = false>
+template <int L, int G, int MINB, bool ROLL, bool NOBK = false, bool LOCK = false>
 __global__ void __launch_bounds__(64 * G, MINB)
 blind_rotate_kernel(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
                     const int32_t *__restrict__ baseB, int32_t *__restrict__ ext)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int grp = threadIdx.x >> 6, tid = threadIdx.x & 63;
-    const int g = blockIdx.x * G + grp;
-    if (g >= ga.ntempl * ga.n_inst) return; /* whole group leaves; groups never share a barrier */
+    int g = blockIdx.x * G + grp;
+    const bool active = g < ga.ntempl * ga.n_inst;
+    if (!LOCK && !active) return; /* whole group leaves; groups never share a barrier */
+    if (!active) g = ga.ntempl * ga.n_inst - 1; /* lock-step CTAs: idle groups shadow the last gate, write nothing */
 
     unsigned char *base = smem_raw + (size_t)grp * kGroupSmem;
     int32_t *acc = reinterpret_cast<int32_t *>(base);
@@ -172,6 +175,9 @@ blind_rotate_kernel(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga,
 
     /* 3. n CMux steps */
     for (int i = 0; i < n; i++) {
+        /* LOCK: all gates of the CTA enter step i together, so BK_i is fetched from L2 once per CTA and the
+         * other groups hit it in L1 */
+        if (LOCK) __syncthreads();
         const int a = abar[i];
         if (a == 0) continue; /* uniform inside the group */
         double s0r[8], s0i[8], s1r[8], s1i[8];
@@ -224,9 +230,258 @@ blind_rotate_kernel(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga,
     }
 
     /* 4. SampleExtract at index 0 */
+    if (!active) return;
     int32_t *o = ext + (size_t)g * kExtStride;
     for (int j = tid; j < kN; j += 64) o[j] = (j == 0) ? acc[0] : -acc[kN - j];
     if (tid == 0) o[kN] = acc[kN];
+}
+
+/* ---- latency variant: one gate per CTA, one 64-thread group per forward transform ----
+ * A circuit level of one expression holds ~45 gates: far too few to fill 148 SMs with the
+ * throughput kernel, so the level time is one gate's latency.  Here the (k+1)l = 2L forward transforms of a
+ * CMux step run in parallel on 2L groups; every group writes its two partial products (one per output
+ * polynomial) into its own exchange buffers; groups 0 and 1 then sum the 2L partials of "their" polynomial,
+ * run the inverse transform and update ACC.  Two CTA barriers per step. */
+constexpr int kWideInvBytes = 2 * kBufBytes; /* private exchange buffers of the two inverse transforms */
+constexpr int wide_smem_bytes(int L) { return kAccBytes + 2 * L * 2 * kBufBytes + kWideInvBytes + kAbarBytes; }
+
+template <int L>
+__global__ void __launch_bounds__(64 * 2 * L, 1)
+blind_rotate_wide_kernel(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
+                         const int32_t *__restrict__ baseB, int32_t *__restrict__ ext)
+{
+    constexpr int NG = 2 * L, NT = 64 * NG;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int grp = threadIdx.x >> 6, tid = threadIdx.x & 63;
+    const int g = blockIdx.x;
+    int32_t *acc = reinterpret_cast<int32_t *>(smem_raw);
+    cd *bufs = reinterpret_cast<cd *>(smem_raw + kAccBytes);                 /* [NG][2][576] */
+    cd *invbuf = reinterpret_cast<cd *>(smem_raw + kAccBytes + NG * 2 * kBufBytes) + (grp & 1) * kBufElems;
+    uint16_t *abar = reinterpret_cast<uint16_t *>(smem_raw + kAccBytes + NG * 2 * kBufBytes + kWideInvBytes);
+    cd *myA = bufs + (size_t)grp * 2 * kBufElems, *myB = myA + kBufElems;
+
+    const int n = p.n;
+    {
+        const int e = g / ga.ntempl, t = g - e * ga.ntempl;
+        GateT gt = ga.uni;
+        if (ga.tmpl) gt = ga.tmpl[t]; else { gt.in0 = (gt.in0 >= 0) ? t : -1; gt.in1 = (gt.in1 >= 0) ? t : -1; }
+        const size_t blk = (size_t)e * ga.inst_samples;
+        const int32_t *in0 = gt.in0 >= 0 ? baseA + (blk + gt.in0) * ga.stride : nullptr;
+        const int32_t *in1 = gt.in1 >= 0 ? baseB + (blk + gt.in1) * ga.stride : nullptr;
+        const int32_t c0 = gt.c0, c1 = gt.c1, cst = gt.cst_mu * p.mu;
+        for (int i = threadIdx.x; i <= n; i += NT) {
+            int32_t v = (i == n) ? cst : 0;
+            if (in0) v += c0 * __ldg(in0 + i);
+            if (in1) v += c1 * __ldg(in1 + i);
+            abar[i] = (uint16_t)modswitch_2N(v);
+        }
+    }
+    __syncthreads();
+    {
+        const int bbar = abar[n];
+        const int a = (2 * kN - bbar) & (2 * kN - 1), ar = a & (kN - 1);
+        const bool flip = a >= kN;
+        for (int j = threadIdx.x; j < kN; j += NT) { acc[j] = 0; acc[kN + j] = ((j < ar) != flip) ? -p.mu : p.mu; }
+    }
+    __syncthreads();
+
+    const Tw w1 = tw_pass1(), w2 = d_tw2[tid >> 3], w3 = d_tw3[tid];
+    const int Bgbit = p.Bgbit;
+    const uint32_t maskBg = (1u << Bgbit) - 1;
+    const int32_t halfBg = 1 << (Bgbit - 1);
+    uint32_t offset = 0;
+#pragma unroll
+    for (int i = 1; i <= L; i++) offset += (uint32_t)halfBg << (32 - i * Bgbit);
+    const int q = grp / L, pp = grp % L, shift = 32 - (pp + 1) * Bgbit;
+    constexpr int kRowElems = 2 * kHalfN, kBkStride = 2 * L * kRowElems;
+
+    for (int i = 0; i < n; i++) {
+        const int a = abar[i];
+        if (a == 0) continue; /* uniform in the CTA */
+        {
+            int32_t c[16];
+            rot_minus_one(acc + q * kN, tid, a, c);
+            double xr[8], xi[8];
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                xr[m] = digit_f64(c[m], offset, shift, maskBg, halfBg);
+                xi[m] = digit_f64(c[8 + m], offset, shift, maskBg, halfBg);
+            }
+            fwd_transform(xr, xi, myA, tid, grp, w1, w2, w3);
+            const double2 *bk_r = bkfft + (size_t)i * kBkStride + (size_t)grp * kRowElems + tid;
+            double2 b0[8], b1[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) { b0[r] = __ldg(bk_r + r * 64); b1[r] = __ldg(bk_r + kHalfN + r * 64); }
+            group_sync(grp); /* every thread of the group has finished reading myA in pass 3 */
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                cd v0, v1;
+                v0.x = xr[r] * b0[r].x - xi[r] * b0[r].y; v0.y = xr[r] * b0[r].y + xi[r] * b0[r].x;
+                v1.x = xr[r] * b1[r].x - xi[r] * b1[r].y; v1.y = xr[r] * b1[r].y + xi[r] * b1[r].x;
+                myA[r * 64 + tid] = v0;
+                myB[r * 64 + tid] = v1;
+            }
+        }
+        __syncthreads();
+        if (grp < 2) {
+            double sr[8], si[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) { sr[r] = 0.0; si[r] = 0.0; }
+            const cd *src = bufs + (size_t)grp * kBufElems + tid; /* bufA of group 0 for j = 0, bufB for j = 1 */
+#pragma unroll
+            for (int gg = 0; gg < NG; gg++)
+#pragma unroll
+                for (int r = 0; r < 8; r++) { const cd v = src[(size_t)gg * 2 * kBufElems + r * 64]; sr[r] += v.x; si[r] += v.y; }
+            inv_transform(sr, si, invbuf, tid, grp, w1, w2, w3);
+            int32_t *accj = acc + grp * kN;
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                accj[tid + 64 * m] += round_to_torus(sr[m]);
+                accj[tid + 64 * m + 512] += round_to_torus(si[m]);
+            }
+        }
+        __syncthreads();
+    }
+    int32_t *o = ext + (size_t)g * kExtStride;
+    for (int j = threadIdx.x; j < kN; j += NT) o[j] = (j == 0) ? acc[0] : -acc[kN - j];
+    if (threadIdx.x == 0) o[kN] = acc[kN];
+}
+
+/* ---- latency variant with two groups per gate: group q owns ACC polynomial q, runs its l forward transforms
+ * with register accumulators for both output polynomials, hands the partial sum of the *other* polynomial to
+ * the other group through 8 KB of shared memory, and inverts / updates its own polynomial.  Per step: 4
+ * transform latencies instead of 8, and only 32 KB of extra shared-memory traffic (the 2l-group kernel above
+ * moves 192 KB and is LSU-bound at 72 %: profiles/README.md). */
+constexpr int pair_smem_bytes() { return kAccBytes + 2 * 2 * kBufBytes + 2 * kHalfN * 16 + kAbarBytes; }
+
+template <int L>
+__global__ void __launch_bounds__(128, 2)
+blind_rotate_pair_kernel(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
+                         const int32_t *__restrict__ baseB, int32_t *__restrict__ ext)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int grp = threadIdx.x >> 6, tid = threadIdx.x & 63;
+    const int g = blockIdx.x;
+    int32_t *acc = reinterpret_cast<int32_t *>(smem_raw);
+    cd *bufA = reinterpret_cast<cd *>(smem_raw + kAccBytes) + (size_t)grp * 2 * kBufElems, *bufB = bufA + kBufElems;
+    cd *xch = reinterpret_cast<cd *>(smem_raw + kAccBytes + 4 * kBufBytes); /* [2][512] */
+    uint16_t *abar = reinterpret_cast<uint16_t *>(smem_raw + kAccBytes + 4 * kBufBytes + 2 * kHalfN * 16);
+
+    const int n = p.n;
+    {
+        const int e = g / ga.ntempl, t = g - e * ga.ntempl;
+        GateT gt = ga.uni;
+        if (ga.tmpl) gt = ga.tmpl[t]; else { gt.in0 = (gt.in0 >= 0) ? t : -1; gt.in1 = (gt.in1 >= 0) ? t : -1; }
+        const size_t blk = (size_t)e * ga.inst_samples;
+        const int32_t *in0 = gt.in0 >= 0 ? baseA + (blk + gt.in0) * ga.stride : nullptr;
+        const int32_t *in1 = gt.in1 >= 0 ? baseB + (blk + gt.in1) * ga.stride : nullptr;
+        const int32_t c0 = gt.c0, c1 = gt.c1, cst = gt.cst_mu * p.mu;
+        for (int i = threadIdx.x; i <= n; i += 128) {
+            int32_t v = (i == n) ? cst : 0;
+            if (in0) v += c0 * __ldg(in0 + i);
+            if (in1) v += c1 * __ldg(in1 + i);
+            abar[i] = (uint16_t)modswitch_2N(v);
+        }
+    }
+    __syncthreads();
+    {
+        const int bbar = abar[n];
+        const int a = (2 * kN - bbar) & (2 * kN - 1), ar = a & (kN - 1);
+        const bool flip = a >= kN;
+        for (int j = threadIdx.x; j < kN; j += 128) { acc[j] = 0; acc[kN + j] = ((j < ar) != flip) ? -p.mu : p.mu; }
+    }
+    __syncthreads();
+
+    const Tw w1 = tw_pass1(), w2 = d_tw2[tid >> 3], w3 = d_tw3[tid];
+    const int Bgbit = p.Bgbit;
+    const uint32_t maskBg = (1u << Bgbit) - 1;
+    const int32_t halfBg = 1 << (Bgbit - 1);
+    uint32_t offset = 0;
+#pragma unroll
+    for (int i = 1; i <= L; i++) offset += (uint32_t)halfBg << (32 - i * Bgbit);
+    constexpr int kRowElems = 2 * kHalfN, kBkStride = 2 * L * kRowElems;
+    int32_t *myacc = acc + grp * kN;
+    int toggle = 0;
+
+    for (int i = 0; i < n; i++) {
+        const int a = abar[i];
+        if (a == 0) continue; /* uniform in the CTA */
+        double mr[8], mi[8], orr[8], oi[8]; /* partial sums of my polynomial / of the other group's */
+#pragma unroll
+        for (int r = 0; r < 8; r++) { mr[r] = 0.0; mi[r] = 0.0; orr[r] = 0.0; oi[r] = 0.0; }
+        const double2 *bk_r = bkfft + (size_t)i * kBkStride + (size_t)grp * L * kRowElems + tid;
+        const double2 *bk_mine = bk_r + grp * kHalfN, *bk_other = bk_r + (1 - grp) * kHalfN;
+        int32_t c[16];
+        rot_minus_one(myacc, tid, a, c);
+#pragma unroll
+        for (int pp = 0; pp < L; pp++) {
+            const int shift = 32 - (pp + 1) * Bgbit;
+            double xr[8], xi[8];
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                xr[m] = digit_f64(c[m], offset, shift, maskBg, halfBg);
+                xi[m] = digit_f64(c[8 + m], offset, shift, maskBg, halfBg);
+            }
+            cd *buf = toggle ? bufB : bufA;
+            toggle ^= 1;
+            fwd_transform(xr, xi, buf, tid, grp, w1, w2, w3);
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const double2 b0 = __ldg(bk_mine + pp * kRowElems + r * 64);
+                const double2 b1 = __ldg(bk_other + pp * kRowElems + r * 64);
+                cmac(mr[r], mi[r], xr[r], xi[r], b0.x, b0.y);
+                cmac(orr[r], oi[r], xr[r], xi[r], b1.x, b1.y);
+            }
+        }
+        /* hand the other polynomial's partial sum over */
+        cd *out = xch + (size_t)grp * kHalfN + tid;
+#pragma unroll
+        for (int r = 0; r < 8; r++) { cd v; v.x = orr[r]; v.y = oi[r]; out[r * 64] = v; }
+        __syncthreads();
+        const cd *in = xch + (size_t)(1 - grp) * kHalfN + tid;
+#pragma unroll
+        for (int r = 0; r < 8; r++) { const cd v = in[r * 64]; mr[r] += v.x; mi[r] += v.y; }
+        cd *buf = toggle ? bufB : bufA;
+        toggle ^= 1;
+        inv_transform(mr, mi, buf, tid, grp, w1, w2, w3);
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            myacc[tid + 64 * m] += round_to_torus(mr[m]);
+            myacc[tid + 64 * m + 512] += round_to_torus(mi[m]);
+        }
+        __syncthreads();
+    }
+    int32_t *o = ext + (size_t)g * kExtStride;
+    for (int j = threadIdx.x; j < kN; j += 128) o[j] = (j == 0) ? acc[0] : -acc[kN - j];
+    if (threadIdx.x == 0) o[kN] = acc[kN];
+}
+
+template <int L>
+static cudaError_t launch_br_pair(const DevParams &p, const double2 *bkfft, const GateAddr &ga, const int32_t *baseA,
+                                  const int32_t *baseB, int32_t *ext, long long count, cudaStream_t s)
+{
+    constexpr int smem = pair_smem_bytes();
+    cudaError_t e = cudaFuncSetAttribute(blind_rotate_pair_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    blind_rotate_pair_kernel<L><<<(int)count, 128, smem, s>>>(p, bkfft, ga, baseA, baseB, ext);
+    return cudaGetLastError();
+}
+
+/* launches of at most this many gates use the latency kernel: 3 waves of 148 one-gate CTAs take about as
+ * long as one wave of the throughput kernel (4 gates per SM) */
+static long long g_wide_max = [] { const char *e = getenv("IEACHE_WIDE_MAX"); return e ? atoll(e) : 296LL; }();
+void set_wide_max(long long v) { g_wide_max = v; }
+long long get_wide_max() { return g_wide_max; }
+
+template <int L>
+static cudaError_t launch_br_wide(const DevParams &p, const double2 *bkfft, const GateAddr &ga, const int32_t *baseA,
+                                  const int32_t *baseB, int32_t *ext, long long count, cudaStream_t s)
+{
+    constexpr int smem = wide_smem_bytes(L);
+    cudaError_t e = cudaFuncSetAttribute(blind_rotate_wide_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    blind_rotate_wide_kernel<L><<<(int)count, 64 * 2 * L, smem, s>>>(p, bkfft, ga, baseA, baseB, ext);
+    return cudaGetLastError();
 }
 
 /* launch configuration: IEACHE_BR_VARIANT selects among the compiled variants (tuning aid) */
@@ -236,18 +491,18 @@ static int br_variant()
     if (v < 0) { const char *e = getenv("IEACHE_BR_VARIANT"); v = e ? atoi(e) : 7; }
     return v;
 }
-int blind_rotate_groups_per_cta() { const int v = br_variant(); return (v == 4) ? 4 : ((v == 0 || v == 1 || v == 3 || v == 5 || v == 6) ? 2 : 1); }
+int blind_rotate_groups_per_cta() { const int v = br_variant(); return (v == 4 || v == 11 || v == 13) ? 4 : ((v == 0 || v == 1 || v == 3 || v == 5 || v == 6 || v == 12) ? 2 : 1); }
 int blind_rotate_smem_bytes(int groups) { return groups * kGroupSmem; }
 
-template <int L, int G, int MINB, bool ROLL, bool NOBK = false>
+template <int L, int G, int MINB, bool ROLL, bool NOBK = false, bool LOCK = false>
 static cudaError_t launch_br_variant(const DevParams &p, const double2 *bkfft, const GateAddr &ga, const int32_t *baseA,
                                      const int32_t *baseB, int32_t *ext, long long count, cudaStream_t s)
 {
     const int smem = G * kGroupSmem;
     const int grid = (int)((count + G - 1) / G);
-    cudaError_t e = cudaFuncSetAttribute(blind_rotate_kernel<L, G, MINB, ROLL, NOBK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(blind_rotate_kernel<L, G, MINB, ROLL, NOBK, LOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    blind_rotate_kernel<L, G, MINB, ROLL, NOBK><<<grid, 64 * G, smem, s>>>(p, bkfft, ga, baseA, baseB, ext);
+    blind_rotate_kernel<L, G, MINB, ROLL, NOBK, LOCK><<<grid, 64 * G, smem, s>>>(p, bkfft, ga, baseA, baseB, ext);
     return cudaGetLastError();
 }
 
@@ -257,6 +512,17 @@ cudaError_t launch_blind_rotate(const DevParams &p, const double2 *bkfft, const 
     const long long count = (long long)ga.ntempl * ga.n_inst;
     if (count <= 0) return cudaSuccess;
     ext += (size_t)ext_base * kExtStride;
+    /* narrow launches (a circuit level of a few expressions): per-gate latency is what matters */
+    if (count <= g_wide_max) {
+        static const int lat = [] { const char *e = getenv("IEACHE_LATENCY_KERNEL"); return e ? atoi(e) : 2; }();
+        if (lat == 6) {
+            if (p.l == 3) return launch_br_wide<3>(p, bkfft, ga, baseA, baseB, ext, count, s);
+            if (p.l == 2) return launch_br_wide<2>(p, bkfft, ga, baseA, baseB, ext, count, s);
+        } else {
+            if (p.l == 3) return launch_br_pair<3>(p, bkfft, ga, baseA, baseB, ext, count, s);
+            if (p.l == 2) return launch_br_pair<2>(p, bkfft, ga, baseA, baseB, ext, count, s);
+        }
+    }
     if (p.l == 2) return launch_br_variant<2, 1, 4, false>(p, bkfft, ga, baseA, baseB, ext, count, s);
     if (p.l != 3) return cudaErrorInvalidValue;
     switch (br_variant()) {
@@ -269,6 +535,9 @@ cudaError_t launch_blind_rotate(const DevParams &p, const double2 *bkfft, const 
     case 8: return launch_br_variant<3, 1, 5, false>(p, bkfft, ga, baseA, baseB, ext, count, s);
     case 9: return launch_br_variant<3, 1, 6, false>(p, bkfft, ga, baseA, baseB, ext, count, s);
     case 10: return launch_br_variant<3, 1, 5, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 11: return launch_br_variant<3, 4, 1, false, false, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 12: return launch_br_variant<3, 2, 2, false, false, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 13: return launch_br_variant<3, 4, 1, false, false, false>(p, bkfft, ga, baseA, baseB, ext, count, s);
     /* timing experiments only (wrong results): no BK loads */
     case 107: return launch_br_variant<3, 1, 4, false, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
     case 109: return launch_br_variant<3, 1, 6, false, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
@@ -340,6 +609,76 @@ keyswitch_kernel(DevParams p, const int32_t *__restrict__ ksk, GateAddr ga, int3
     }
 }
 
+/* latency variant for narrow launches: a cluster of 8 CTAs per gate, each gathering the rows of 128 of the
+ * 1024 positions; the partial sums meet in CTA 0 through distributed shared memory.  Integer adds commute,
+ * so the result is bit-identical to keyswitch_kernel's. */
+constexpr int kKsCluster = 8;
+__global__ void __cluster_dims__(kKsCluster, 1, 1) __launch_bounds__(kKsThreads)
+keyswitch_cluster_kernel(DevParams p, const int32_t *__restrict__ ksk, GateAddr ga, int32_t *__restrict__ out_base,
+                         const int32_t *__restrict__ ext, int pair_offset, int32_t cst_post)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ int32_t rows[(kN / kKsCluster) * 16];
+    __shared__ __align__(16) int4 partial[kLweStride / 4];
+    __shared__ int s_nrows;
+    const int g = blockIdx.x / kKsCluster, part = (int)cluster.block_rank(), tid = threadIdx.x;
+    const int e = g / ga.ntempl, tt = g - e * ga.ntempl;
+    const int out_idx = ga.tmpl ? ga.tmpl[tt].out : tt;
+    int32_t *outp = out_base + ((size_t)e * ga.inst_samples + out_idx) * ga.stride;
+    const int t = p.ks_t, basebit = p.ks_basebit, basem1 = (1 << basebit) - 1;
+    const uint32_t prec_offset = 1u << (32 - (1 + basebit * t));
+    const int32_t *u0 = ext + (size_t)g * kExtStride;
+    const int32_t *u1 = pair_offset > 0 ? ext + ((size_t)g + pair_offset) * kExtStride : nullptr;
+    if (tid == 0) s_nrows = 0;
+    __syncthreads();
+    constexpr int kPer = kN / kKsCluster;
+    for (int ii = tid; ii < kPer; ii += kKsThreads) {
+        const int i = part * kPer + ii;
+        uint32_t a = (uint32_t)u0[i];
+        if (u1) a += (uint32_t)u1[i];
+        a += prec_offset;
+        for (int j = 0; j < t; j++) {
+            const int d = (a >> (32 - (j + 1) * basebit)) & basem1;
+            if (d) rows[atomicAdd(&s_nrows, 1)] = (i * t + j) * basem1 + (d - 1);
+        }
+    }
+    __syncthreads();
+    const int nrows = s_nrows;
+    int4 accv = make_int4(0, 0, 0, 0);
+    if (tid < kLweStride / 4) {
+        const int4 *kv = reinterpret_cast<const int4 *>(ksk) + tid;
+        int r = 0;
+        for (; r + 8 <= nrows; r += 8) {
+            int4 v[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) v[q] = __ldg(kv + (size_t)rows[r + q] * (kLweStride / 4));
+#pragma unroll
+            for (int q = 0; q < 8; q++) { accv.x -= v[q].x; accv.y -= v[q].y; accv.z -= v[q].z; accv.w -= v[q].w; }
+        }
+        for (; r < nrows; r++) {
+            const int4 v = __ldg(kv + (size_t)rows[r] * (kLweStride / 4));
+            accv.x -= v.x; accv.y -= v.y; accv.z -= v.z; accv.w -= v.w;
+        }
+        partial[tid] = accv;
+    }
+    cluster.sync();
+    if (part == 0 && tid < kLweStride / 4) {
+        for (int r = 1; r < kKsCluster; r++) {
+            const int4 v = cluster.map_shared_rank(partial, r)[tid];
+            accv.x += v.x; accv.y += v.y; accv.z += v.z; accv.w += v.w;
+        }
+        const int32_t bval = u0[kN] + (u1 ? u1[kN] : 0) + cst_post;
+        const int w0 = tid * 4;
+        if (p.n >= w0 && p.n < w0 + 4) {
+            if (p.n == w0) accv.x += bval; else if (p.n == w0 + 1) accv.y += bval;
+            else if (p.n == w0 + 2) accv.z += bval; else accv.w += bval;
+        }
+        reinterpret_cast<int4 *>(outp)[tid] = accv;
+    }
+    cluster.sync(); /* keep every CTA's shared memory alive until CTA 0 has read it */
+}
+
 cudaError_t launch_keyswitch(const DevParams &p, const int32_t *ksk, const GateAddr &ga, int32_t *out_base,
                              const int32_t *ext, int pair_offset, int32_t cst_post, cudaStream_t s)
 {
@@ -353,6 +692,10 @@ cudaError_t launch_keyswitch(const DevParams &p, const int32_t *ksk, const GateA
         attr_set = true;
     }
     if (smem > 64 * 1024) return cudaErrorInvalidValue;
+    if (count <= g_wide_max && p.ks_t <= 16) {
+        keyswitch_cluster_kernel<<<(unsigned)count * kKsCluster, kKsThreads, 0, s>>>(p, ksk, ga, out_base, ext, pair_offset, cst_post);
+        return cudaGetLastError();
+    }
     keyswitch_kernel<<<(unsigned)count, kKsThreads, smem, s>>>(p, ksk, ga, out_base, ext, pair_offset, cst_post);
     return cudaGetLastError();
 }

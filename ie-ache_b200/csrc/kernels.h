@@ -76,6 +76,10 @@ cudaError_t launch_circuit_gather_outputs(int32_t *outputs, const int32_t *wires
 /* dense FP64 FMA microbenchmark (best of 3), TFLOP/s */
 cudaError_t launch_fp64_peak(cudaStream_t s, double *tflops);
 
+/* launches with <= wide_max gates use the latency kernel (one gate per CTA, 2l groups) */
+void set_wide_max(long long v);
+long long get_wide_max();
+
 int blind_rotate_smem_bytes(int groups);
 int blind_rotate_groups_per_cta();
 

@@ -66,6 +66,10 @@ int ieache_ctx_kernel_times(ieache_ctx *ctx, double *blind_rotate_ms, double *ke
                             uint64_t *blind_rotate_launches, uint64_t *keyswitch_launches, int reset);
 int ieache_ctx_set_timing(ieache_ctx *ctx, int enabled);
 
+/* Kernel selection: launches of at most `max_gates` gates use the latency variant of the blind rotation
+ * (one gate per CTA, one thread group per forward transform), larger ones the throughput variant.
+ * Process-wide; returns the previous value; a negative argument only queries.  Default 296 (two waves of one-gate CTAs on 148 SMs). */
+int64_t ieache_set_wide_max(int64_t max_gates);
 /* step timer: CUDA events on the engine's stream (torch events only see torch's stream) */
 int ieache_ctx_timer_start(ieache_ctx *ctx);
 int ieache_ctx_timer_stop(ieache_ctx *ctx, double *elapsed_ms); /* records, synchronises, returns the elapsed device time */

@@ -52,9 +52,17 @@ def small(pkg, oracle, eng):
     key.close(); ks.free(); nbit.free()
 
 
+@pytest.fixture(params=["latency_kernel", "throughput_kernel"])
+def kernel_mode(pkg, request):
+    """both blind-rotation kernels must pass the same parity tests whatever the launch size"""
+    old = pkg.set_wide_max(1 << 40 if request.param == "latency_kernel" else 0)
+    yield request.param
+    pkg.set_wide_max(old)
+
+
 # ------------------------------------------------------------------ gates
 @pytest.mark.parametrize("op", BIN_OPS + ["MUX"])
-def test_gate_parity_default_params(eng, full, op):
+def test_gate_parity_default_params(eng, full, op, kernel_mode):
     ks, key = full
     rng = np.random.default_rng(abs(hash(op)) % 1000)
     ba, bb, bc = (rng.integers(0, 2, 16).astype(np.int32) for _ in range(3))
@@ -76,7 +84,7 @@ def test_free_gates_are_exact(eng, full):
     assert (c0[:, 630] == -(1 << 29)).all()
 
 
-def test_golden_vectors(pkg, oracle, eng):
+def test_golden_vectors(pkg, oracle, eng, kernel_mode):
     g = np.load(os.path.join(ROOT, "tests", "golden", "gates_n16_seed4242.npz"))
     ks = oracle.keygen(ob.params_default(int(g["n"])), seed=int(g["seed"]))
     key = eng.cloud_key_from_arrays(pkg.Params.default(int(g["n"])), ks.bk_coef(), ks.ksk())
@@ -89,7 +97,7 @@ def test_golden_vectors(pkg, oracle, eng):
     key.close(); ks.free()
 
 
-def test_stage_parity(eng, full):
+def test_stage_parity(eng, full, kernel_mode):
     """blind rotation + extraction against the oracle (phase tolerance), key switch bit-exact"""
     ks, key = full
     a, b = ks.encrypt([1, 0, 1, 1, 0, 1, 0, 0], 1), ks.encrypt([1, 1, 0, 1, 0, 0, 1, 0], 2)
@@ -102,7 +110,7 @@ def test_stage_parity(eng, full):
     assert (eng.keyswitch(key, ext_cpu) == ks.keyswitch(ext_cpu)).all()  # integer path: bit-exact
 
 
-def test_aliasing_and_empty(eng, full):
+def test_aliasing_and_empty(eng, full, kernel_mode):
     ks, key = full
     a, b = ks.encrypt([1, 1, 0], 1), ks.encrypt([1, 0, 0], 2)
     out = eng.gate_batch(key, "AND", a, b)
@@ -168,7 +176,7 @@ def _decode(ks, out, nwords):
 
 
 @pytest.mark.parametrize("kind,width", [(1, 32), (1, 64), (1, 256), (2, 32), (2, 128), (4, 32), (5, 32)])
-def test_circuits_default_params_vs_integers(pkg, eng, full, kind, width):
+def test_circuits_default_params_vs_integers(pkg, eng, full, kind, width, kernel_mode):
     ks, key = full
     nc = width // 32
     circ = eng.circuit(kind, width)
@@ -205,7 +213,7 @@ def test_wide_multipliers_small_params(pkg, eng, small, width):
     assert _decode(ks, out[0], 2 * nc) == a * b
 
 
-def test_mul32_matches_oracle_circuit(eng, small):
+def test_mul32_matches_oracle_circuit(eng, small, kernel_mode):
     """the same mul32 on the oracle (11 264 gate calls, in cloud.c's order) and on the GPU (255 levels)"""
     ks, _, key = small
     a, b = 0x9E3779B9, 0x7F4A7C15
