@@ -57,6 +57,7 @@ struct ieache_ctx {
      * SLOWER (92k vs 98k gates/s) — its gather stream evicts the bootstrapping key from L2 and its CTAs
      * displace blind-rotation CTAs — so the overlap is off unless IEACHE_OVERLAP_KS=1 */
     bool overlap_ks = false;
+    const void *persist_key = nullptr;
     uint64_t launches = 0;
     int32_t *d_ext = nullptr; size_t ext_cap = 0;      /* extracted samples scratch */
     int32_t *d_stage[4] = {nullptr, nullptr, nullptr, nullptr}; size_t stage_cap[4] = {0, 0, 0, 0};
@@ -425,11 +426,35 @@ extern "C" int ieache_sym_decrypt_device(ieache_ctx *ctx, const ieache_secretkey
     return IEACHE_OK;
 }
 
+/* Optional (IEACHE_L2_PERSIST=1): pin the transform-domain bootstrapping key in L2 for launches on the
+ * blind-rotation stream, so that key-switch traffic cannot evict it. */
+static int apply_l2_persist(ieache_ctx *ctx, const ieache_cloudkey *key)
+{
+    static const int want = [] { const char *e = getenv("IEACHE_L2_PERSIST"); return e ? atoi(e) : 0; }();
+    if (!want || ctx->persist_key == key->bkfft) return IEACHE_OK;
+    int max_win = 0, max_persist = 0;
+    CU(cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device));
+    CU(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device));
+    const size_t bytes = std::min<size_t>(key->bkfft_bytes, (size_t)max_win);
+    CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(bytes, (size_t)max_persist)));
+    cudaStreamAttrValue attr{};
+    attr.accessPolicyWindow.base_ptr = key->bkfft;
+    attr.accessPolicyWindow.num_bytes = bytes;
+    attr.accessPolicyWindow.hitRatio = std::min(1.0f, (float)max_persist / (float)bytes);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    CU(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    ctx->persist_key = key->bkfft;
+    if (want > 1) fprintf(stderr, "ieache: L2 persist window %zu B, max persisting %d B, max window %d B\n", bytes, max_persist, max_win);
+    return IEACHE_OK;
+}
+
 /* ------------------------------------------------------------------ launches with optional timing */
 static int run_br(ieache_ctx *ctx, const ieache_cloudkey *key, const GateAddr &ga, const int32_t *A, const int32_t *B, int ext_base,
                   int32_t *ext = nullptr)
 {
     TimedLaunch t{};
+    { int rcp = apply_l2_persist(ctx, key); if (rcp) return rcp; }
     if (ctx->timing) { CU(cudaEventCreate(&t.a)); CU(cudaEventCreate(&t.b)); t.kind = 0; CU(cudaEventRecord(t.a, ctx->stream)); }
     CU(launch_blind_rotate(key->dp, key->bkfft, ga, A, B, ext ? ext : ctx->d_ext, ext_base, ctx->stream));
     if (ctx->timing) { CU(cudaEventRecord(t.b, ctx->stream)); ctx->timed.push_back(t); }

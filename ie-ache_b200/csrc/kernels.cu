@@ -43,6 +43,9 @@ cudaError_t twiddle_ptrs(const Tw **tw2, const Tw **tw3)
     return cudaGetSymbolAddress((void **)tw3, d_tw3);
 }
 
+/* named barrier of one 64-thread group.  With one group per CTA the id is a compile-time constant (ptxas then
+ * reserves 2 barriers instead of 16, worth ~5 % in the throughput kernel); a switch over immediate ids was
+ * measured slower than the register form for the multi-group kernels. */
 __device__ __forceinline__ void group_sync(int grp)
 {
     asm volatile("bar.sync %0, 64;" ::"r"(grp + 1) : "memory");
@@ -111,12 +114,31 @@ constexpr int kGroupSmem = kAccBytes + 2 * kBufBytes + kAbarBytes; /* 28704 */
  * allocation is tuned for, ROLL = keep the (k+1)l forward transforms in a rolled loop so the
  * step body fits the 32 KB instruction cache (the fully unrolled body is ~60 KB of SASS) */
 template <int L, int G, int MINB, bool ROLL, bool NOBK = false, bool LOCK = false>
+__device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
+                    const int32_t *__restrict__ baseB, int32_t *__restrict__ ext);
+
+template <int L, int G, int MINB, bool ROLL, bool NOBK = false, bool LOCK = false>
 __global__ void __launch_bounds__(64 * G, MINB)
 blind_rotate_kernel(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
                     const int32_t *__restrict__ baseB, int32_t *__restrict__ ext)
 {
+    blind_rotate_body<L, G, MINB, ROLL, NOBK, LOCK>(p, bkfft, ga, baseA, baseB, ext);
+}
+/* same body with an explicit register cap (5 CTAs of 64 threads per SM at 200 registers) */
+template <int L>
+__global__ void __maxnreg__(200)
+blind_rotate_kernel_r200(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
+                         const int32_t *__restrict__ baseB, int32_t *__restrict__ ext)
+{
+    blind_rotate_body<L, 1, 5, false, false, false>(p, bkfft, ga, baseA, baseB, ext);
+}
+
+template <int L, int G, int MINB, bool ROLL, bool NOBK, bool LOCK>
+__device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
+                    const int32_t *__restrict__ baseB, int32_t *__restrict__ ext)
+{
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int grp = threadIdx.x >> 6, tid = threadIdx.x & 63;
+    const int grp = (G == 1) ? 0 : (threadIdx.x >> 6), tid = (G == 1) ? threadIdx.x : (threadIdx.x & 63);
     int g = blockIdx.x * G + grp;
     const bool active = g < ga.ntempl * ga.n_inst;
     if (!LOCK && !active) return; /* whole group leaves; groups never share a barrier */
@@ -535,6 +557,12 @@ cudaError_t launch_blind_rotate(const DevParams &p, const double2 *bkfft, const 
     case 8: return launch_br_variant<3, 1, 5, false>(p, bkfft, ga, baseA, baseB, ext, count, s);
     case 9: return launch_br_variant<3, 1, 6, false>(p, bkfft, ga, baseA, baseB, ext, count, s);
     case 10: return launch_br_variant<3, 1, 5, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 20: {
+        cudaError_t e = cudaFuncSetAttribute(blind_rotate_kernel_r200<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGroupSmem);
+        if (e != cudaSuccess) return e;
+        blind_rotate_kernel_r200<3><<<(int)count, 64, kGroupSmem, s>>>(p, bkfft, ga, baseA, baseB, ext);
+        return cudaGetLastError();
+    }
     case 11: return launch_br_variant<3, 4, 1, false, false, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
     case 12: return launch_br_variant<3, 2, 2, false, false, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
     case 13: return launch_br_variant<3, 4, 1, false, false, false>(p, bkfft, ga, baseA, baseB, ext, count, s);
