@@ -101,6 +101,13 @@ def lib() -> ctypes.CDLL:
     L.ieache_measure_fp64_peak.argtypes = [c_void_p, POINTER(c_double)]
     L.ieache_host_alloc.argtypes = [c_size_t, POINTER(c_void_p)]
     L.ieache_host_free.argtypes = [c_void_p]
+    L.ieache_session_open.argtypes = [c_void_p, c_char_p, c_char_p, POINTER(c_void_p)]
+    L.ieache_session_open_keys.argtypes = [c_void_p, c_void_p, c_void_p, POINTER(c_void_p)]
+    L.ieache_session_close.argtypes = [c_void_p]
+    L.ieache_session_params.argtypes = [c_void_p, POINTER(Params)]
+    L.ieache_session_compute.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, POINTER(c_size_t), POINTER(c_double)]
+    L.ieache_session_compute_batch.argtypes = [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_double)]
+    L.ieache_session_eval_postfix.argtypes = [c_void_p, c_char_p, c_size_t, c_void_p, c_int, c_void_p, c_void_p, POINTER(c_double)]
     L.ieache_keygen.argtypes = [c_void_p, POINTER(Params), c_uint64, POINTER(c_void_p), POINTER(c_void_p), c_void_p, c_void_p]
     L.ieache_secretkey_import.argtypes = [c_void_p, POINTER(Params), c_void_p, c_void_p, POINTER(c_void_p)]
     L.ieache_secretkey_export.argtypes = [c_void_p, c_void_p, c_void_p]
@@ -125,7 +132,7 @@ def _ptr(a):
     if a is None:
         return None
     if isinstance(a, np.ndarray):
-        assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"]
+        assert a.dtype in (np.int32, np.uint32) and a.flags["C_CONTIGUOUS"]
         return a.ctypes.data_as(c_void_p)
     return c_void_p(int(a))  # raw device/host address
 
@@ -206,6 +213,56 @@ class SecretKey:
     def close(self):
         if self._h:
             lib().ieache_secretkey_destroy(self._h)
+            self._h = None
+
+
+class Session:
+    """Cloud-node session: cloud.key and nbit.key loaded once, then any number of operators
+    (Cloud/cloud.c main() per operator, Cloud/dragonfly_cipher_cloud.py:685-729 for whole expressions)."""
+
+    def __init__(self, engine: "Engine", handle: c_void_p):
+        self.engine, self._h = engine, handle
+        self.params = Params()
+        _check(lib().ieache_session_params(handle, byref(self.params)))
+
+    def compute(self, op: int, operand1: np.ndarray, operand2: np.ndarray):
+        """one operator on two 352-sample client blocks -> (exit_code, answer block, seconds)"""
+        w = self.params.n + 1
+        ans = np.zeros((352, w), dtype=np.int32)
+        cnt, secs = c_size_t(), c_double()
+        rc = lib().ieache_session_compute(self._h, op, _ptr(np.ascontiguousarray(operand1)), _ptr(np.ascontiguousarray(operand2)),
+                                          _ptr(ans), byref(cnt), byref(secs))
+        _check(rc)
+        return rc, ans[:cnt.value], secs.value
+
+    def compute_batch(self, ops, operands1: np.ndarray, operands2: np.ndarray):
+        """`len(ops)` independent requests, batched per circuit -> (exit_codes, answers, counts, seconds)"""
+        n, w = len(ops), self.params.n + 1
+        ops = np.ascontiguousarray(ops, dtype=np.int32)
+        ans = np.zeros((n, 352, w), dtype=np.int32)
+        codes = np.zeros(n, dtype=np.int32)
+        counts = np.zeros(n, dtype=np.uint64)
+        secs = c_double()
+        _check(lib().ieache_session_compute_batch(self._h, n, _ptr(ops), _ptr(np.ascontiguousarray(operands1)),
+                                                  _ptr(np.ascontiguousarray(operands2)), _ptr(ans), _ptr(codes),
+                                                  counts.ctypes.data_as(c_void_p), byref(secs)))
+        return codes, ans, counts, secs.value
+
+    def eval_postfix(self, postfix: str, operands: np.ndarray):
+        """operands: (n_expr, n_operands, 352, n+1); e.g. postfix "AB*C+" -> (exit_code, answers, counts, seconds)"""
+        n_expr, n_ops = operands.shape[0], operands.shape[1]
+        w = self.params.n + 1
+        ans = np.zeros((n_expr, 352, w), dtype=np.int32)
+        counts = np.zeros(n_expr, dtype=np.uint64)
+        secs = c_double()
+        rc = lib().ieache_session_eval_postfix(self._h, postfix.encode(), n_expr, _ptr(np.ascontiguousarray(operands)), n_ops,
+                                               _ptr(ans), counts.ctypes.data_as(c_void_p), byref(secs))
+        _check(rc)
+        return rc, ans, counts, secs.value
+
+    def close(self):
+        if self._h:
+            lib().ieache_session_close(self._h)
             self._h = None
 
 
@@ -316,6 +373,17 @@ class Engine:
 
     def eval_device(self, key: CloudKey, circ: Circuit, in_dev: int, out_dev: int, n_expr: int):
         _check(lib().ieache_circuit_eval_device(self._h, key._h, circ._h, c_void_p(in_dev), c_void_p(out_dev), n_expr))
+
+    def session(self, cloud_key_path: str, nbit_key_path: str) -> Session:
+        h = c_void_p()
+        _check(lib().ieache_session_open(self._h, cloud_key_path.encode(), nbit_key_path.encode(), byref(h)))
+        return Session(self, h)
+
+    def session_from_keys(self, key: CloudKey, nbit_lwe_key: np.ndarray) -> Session:
+        h = c_void_p()
+        k = np.ascontiguousarray(nbit_lwe_key, dtype=np.int32)
+        _check(lib().ieache_session_open_keys(self._h, key._h, _ptr(k), byref(h)))
+        return Session(self, h)
 
     # ---- the ./cloud process contract ---------------------------------------------------------
     def cloud_run(self, directory: str) -> tuple[int, float]:

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <chrono>
+#include <map>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -757,22 +758,205 @@ static void enc32(const HostKeySet &k, int32_t v, int32_t *blk)
     sym_encrypt_bits(k, bits, 32, blk);
 }
 
+/* ---- session: keys loaded once, any number of operators ---------------------------
+ * The reference starts ./cloud once per operator and each start re-parses cloud.key (114 MB) and rebuilds
+ * bkFFT (Cloud/cloud.c:656-663); intermediate results travel through answer.data -> cloud.data on disk
+ * (Cloud/dragonfly_cipher_cloud.py:1306-1327).  A session keeps the device key and the nbit key, evaluates
+ * batches of requests (grouped by circuit) in one levelised pass, and chains operators in memory. */
+struct ieache_session {
+    ieache_ctx *ctx = nullptr;
+    ieache_cloudkey *key = nullptr;
+    bool owns_key = false;
+    HostKeySet nbit;
+    std::map<std::pair<int, int>, ieache_circuit *> circuits;
+};
+
+extern "C" void ieache_session_close(ieache_session *s)
+{
+    if (!s) return;
+    for (auto &kv : s->circuits) ieache_circuit_destroy(kv.second);
+    if (s->owns_key) ieache_cloudkey_destroy(s->key);
+    delete s;
+}
+extern "C" int ieache_session_open_keys(ieache_ctx *ctx, ieache_cloudkey *key, const int32_t *nbit_lwe_key, ieache_session **out)
+{
+    if (!ctx || !key || !nbit_lwe_key || !out) return fail(IEACHE_ERR_ARG, "null argument");
+    ieache_session *s = new ieache_session();
+    s->ctx = ctx; s->key = key; s->owns_key = false;
+    s->nbit.p = key->p; s->nbit.has_secret = true;
+    s->nbit.lwe_key.assign(nbit_lwe_key, nbit_lwe_key + key->p.n);
+    *out = s;
+    return IEACHE_OK;
+}
+extern "C" int ieache_session_open(ieache_ctx *ctx, const char *cloud_key_path, const char *nbit_key_path, ieache_session **out)
+{
+    if (!ctx || !cloud_key_path || !nbit_key_path || !out) return fail(IEACHE_ERR_ARG, "null argument");
+    std::unique_ptr<ieache_session, void (*)(ieache_session *)> s(new ieache_session(), ieache_session_close);
+    s->ctx = ctx;
+    int rc = ieache_cloudkey_load_file(ctx, cloud_key_path, &s->key);          /* cloud.c:656-658 */
+    if (rc) return rc;
+    s->owns_key = true;
+    std::string msg;
+    if ((rc = read_keyset(nbit_key_path, s->nbit, false, msg))) return fail(rc, "%s", msg.c_str());   /* cloud.c:661-663 */
+    if (!s->nbit.has_secret) return fail(IEACHE_ERR_FORMAT, "nbit.key holds no secret key");
+    if (s->nbit.p.n != s->key->p.n) return fail(IEACHE_ERR_UNSUPPORTED, "nbit.key and cloud.key use different n (%d vs %d)", s->nbit.p.n, s->key->p.n);
+    *out = s.release();
+    return IEACHE_OK;
+}
+extern "C" int ieache_session_params(const ieache_session *s, ieache_params *out)
+{
+    if (!s || !out) return fail(IEACHE_ERR_ARG, "null argument");
+    *out = s->key->p;
+    return IEACHE_OK;
+}
+
+struct Request { int kind = 0, width = 0; bool swap = false; };
+
+/* `count` requests (operator + two 352-sample client blocks each) -> `count` answer blocks.
+ * Metadata handling is Cloud/cloud.c:709-864 per request; requests that need the same circuit are
+ * evaluated together, level by level. exit_codes[i] = 0 or 126; answer_counts[i] = 352 or 64 samples. */
+extern "C" int ieache_session_compute_batch(ieache_session *s, size_t count, const int32_t *ops, const int32_t *operands1,
+                                            const int32_t *operands2, int32_t *answers, int32_t *exit_codes, size_t *answer_counts,
+                                            double *seconds)
+{
+    if (!s || !ops || !operands1 || !operands2 || !answers) return fail(IEACHE_ERR_ARG, "null argument");
+    const int n = s->key->p.n;
+    const size_t w = n + 1, B = 32 * w, blk = 352 * w;
+    std::vector<Request> req(count);
+    std::map<std::pair<int, int>, std::vector<size_t>> groups; /* (kind | swap<<8, width) -> request indices */
+    for (size_t i = 0; i < count; i++) {
+        const int32_t *o1 = operands1 + i * blk, *o2 = operands2 + i * blk;
+        int32_t *ans = answers + i * blk;
+        const int int_op = ops[i];
+        const int32_t int_bit1 = dec32(s->nbit, o1 + B), int_bit2 = dec32(s->nbit, o2 + B);   /* cloud.c:709-746 */
+        int32_t n1 = dec32(s->nbit, o1);
+        const int32_t n2 = dec32(s->nbit, o2);                                               /* cloud.c:780-796 */
+        if (n1 == 2) n1 = 1;
+        const int32_t int_negative = n1 + n2;
+        enc32(s->nbit, int_negative == 3 ? 4 : int_negative, ans);                           /* cloud.c:812-826 */
+        int32_t int_bit;
+        if (int_op == 4) { int_bit = std::max(int_bit1, int_bit2); enc32(s->nbit, int_bit * 2, ans + B); }   /* cloud.c:833-843 */
+        else if (int_bit1 >= int_bit2) { int_bit = int_bit1; memcpy(ans + B, o1 + B, B * 4); }
+        else { int_bit = int_bit2; memcpy(ans + B, o2 + B, B * 4); }
+        if (exit_codes) exit_codes[i] = 0;
+        if (answer_counts) answer_counts[i] = 64;
+        Request &r = req[i];
+        r.width = int_bit;
+        if (int_op == 4 && int_bit >= 256) { if (exit_codes) exit_codes[i] = 126; continue; }             /* cloud.c:860-864 */
+        if ((int_op == 1 && int_negative != 1 && int_negative != 2) || (int_op == 2 && (int_negative == 1 || int_negative == 2)))
+            r.kind = IEACHE_CIRC_ADD;                                                                    /* cloud.c:870 */
+        else if (int_op == 2 || (int_op == 1 && (int_negative == 1 || int_negative == 2))) {
+            r.kind = IEACHE_CIRC_SUB;                                                                    /* cloud.c:1194 */
+            r.swap = !((int_op == 2 && int_negative == 0) || (int_op == 1 && int_negative == 2));        /* cloud.c:1196,1809 */
+        } else if (int_op == 4) r.kind = IEACHE_CIRC_MUL;                                                /* cloud.c:2368 */
+        if (!r.kind) continue;
+        const bool ok_width = (r.kind == IEACHE_CIRC_MUL) ? (int_bit == 32 || int_bit == 64 || int_bit == 128)
+                                                          : (int_bit == 32 || int_bit == 64 || int_bit == 128 || int_bit == 256);
+        if (!ok_width) { r.kind = 0; continue; }          /* the reference computes nothing for other widths */
+        groups[{r.kind | (r.swap ? 256 : 0), int_bit}].push_back(i);
+    }
+    double secs = 0;
+    for (auto &kv : groups) {
+        const int kind = kv.first.first & 255, width = kv.first.second;
+        const bool swap_ops = (kv.first.first & 256) != 0;
+        const std::vector<size_t> &idx = kv.second;
+        ieache_circuit *&circ = s->circuits[{kind, width}];
+        int rc;
+        if (!circ && (rc = ieache_circuit_build(kind, width, &circ))) return rc;
+        const int nc = width / 32;
+        const size_t nin = circ->c.n_inputs, nout = circ->c.outputs.size();
+        std::vector<int32_t> in(idx.size() * nin * w), out(idx.size() * nout * w);
+        for (size_t e = 0; e < idx.size(); e++) {
+            const int32_t *o1 = operands1 + idx[e] * blk, *o2 = operands2 + idx[e] * blk;
+            int32_t *dst = &in[e * nin * w];
+            memcpy(dst, (swap_ops ? o2 : o1) + 2 * B, (size_t)nc * B * 4);
+            memcpy(dst + (size_t)nc * B, (swap_ops ? o1 : o2) + 2 * B, (size_t)nc * B * 4);
+            memcpy(dst + (size_t)2 * nc * B, o1 + 10 * B, B * 4);                 /* ciphertextcarry1 */
+        }
+        const auto t0 = std::chrono::steady_clock::now();
+        if ((rc = ieache_circuit_eval(s->ctx, s->key, circ, in.data(), out.data(), idx.size()))) return rc;
+        secs += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        const size_t nres = nout / 32;
+        for (size_t e = 0; e < idx.size(); e++) {
+            const int32_t *carry1 = operands1 + idx[e] * blk + 10 * B;
+            int32_t *ans = answers + idx[e] * blk;
+            for (size_t q = 0; q < 8; q++) memcpy(ans + (2 + q) * B, q < nres ? &out[(e * nout + q * 32) * w] : carry1, B * 4);   /* cloud.c:899-916 */
+            memcpy(ans + 10 * B, carry1, B * 4);
+            if (answer_counts) answer_counts[idx[e]] = 352;
+        }
+    }
+    if (seconds) *seconds = secs;
+    return IEACHE_OK;
+}
+
+extern "C" int ieache_session_compute(ieache_session *s, int op, const int32_t *operand1, const int32_t *operand2, int32_t *answer,
+                                      size_t *answer_count, double *seconds)
+{
+    int32_t code = 0;
+    const int32_t op32 = op;
+    int rc = ieache_session_compute_batch(s, 1, &op32, operand1, operand2, answer, &code, answer_count, seconds);
+    return rc ? rc : code;
+}
+
+/* A whole postfix expression per instance, e.g. "AB*C+" (Output/output_dynamic.py builds it; the Cloud walks
+ * it at Cloud/dragonfly_cipher_cloud.py:685-729).  Letters index the operand blocks (A = 0), operators are
+ * + - * (opcodes 1, 2, 4).  Operand order follows the infix expression exactly as the reference's `flip`
+ * logic does.  All instances share the postfix string; each operator is one batched compute over all
+ * instances.  Stops early (returns 126) if any instance hits the 256-bit multiply abort, like the reference. */
+extern "C" int ieache_session_eval_postfix(ieache_session *s, const char *postfix, size_t n_expr, const int32_t *operands,
+                                           int n_operands, int32_t *answers, size_t *answer_counts, double *seconds)
+{
+    if (!s || !postfix || !operands || !answers) return fail(IEACHE_ERR_ARG, "null argument");
+    const size_t w = s->key->p.n + 1, blk = 352 * w;
+    std::vector<std::vector<int32_t>> pool;          /* intermediate results, [n_expr][352][w] each */
+    std::vector<const int32_t *> stack_ptr;           /* base pointer of a stacked value */
+    std::vector<size_t> stack_stride;                 /* distance between instances */
+    double secs = 0;
+    int last_code = 0;
+    for (const char *c = postfix; *c; ++c) {
+        if (*c == ' ') continue;
+        if (*c >= 'A' && *c <= 'Z') {
+            const int k = *c - 'A';
+            if (k >= n_operands) return fail(IEACHE_ERR_ARG, "postfix names operand %c but only %d were given", *c, n_operands);
+            stack_ptr.push_back(operands + (size_t)k * blk);
+            stack_stride.push_back((size_t)n_operands * blk);
+            continue;
+        }
+        const int op = *c == '+' ? 1 : *c == '-' ? 2 : *c == '*' ? 4 : 0;
+        if (!op) return fail(IEACHE_ERR_ARG, "unknown token '%c' in postfix expression", *c);
+        if (stack_ptr.size() < 2) return fail(IEACHE_ERR_ARG, "malformed postfix expression");
+        const int32_t *b = stack_ptr.back(); const size_t bs = stack_stride.back(); stack_ptr.pop_back(); stack_stride.pop_back();
+        const int32_t *a = stack_ptr.back(); const size_t as = stack_stride.back(); stack_ptr.pop_back(); stack_stride.pop_back();
+        std::vector<int32_t> o1(n_expr * blk), o2(n_expr * blk), ops(n_expr, op), codes(n_expr);
+        for (size_t e = 0; e < n_expr; e++) { memcpy(&o1[e * blk], a + e * as, blk * 4); memcpy(&o2[e * blk], b + e * bs, blk * 4); }
+        pool.emplace_back(n_expr * blk);
+        std::vector<size_t> counts(n_expr);
+        double t = 0;
+        int rc = ieache_session_compute_batch(s, n_expr, ops.data(), o1.data(), o2.data(), pool.back().data(), codes.data(), counts.data(), &t);
+        if (rc) return rc;
+        secs += t;
+        for (size_t e = 0; e < n_expr; e++) if (codes[e]) last_code = codes[e];
+        stack_ptr.push_back(pool.back().data());
+        stack_stride.push_back(blk);
+        if (answer_counts) for (size_t e = 0; e < n_expr; e++) answer_counts[e] = counts[e];
+        if (last_code) break;      /* dragonfly_cipher_cloud.py:1295-1297: send the short answer and stop */
+    }
+    if (stack_ptr.empty()) return fail(IEACHE_ERR_ARG, "empty postfix expression");
+    for (size_t e = 0; e < n_expr; e++) memcpy(answers + e * blk, stack_ptr.back() + e * stack_stride.back(), blk * 4);
+    if (seconds) *seconds = secs;
+    return last_code;
+}
+
 extern "C" int ieache_cloud_run(ieache_ctx *ctx, const char *dir, double *seconds)
 {
     if (!ctx || !dir) return fail(IEACHE_ERR_ARG, "null argument");
     const std::string d(dir);
-    std::string msg;
     int rc;
-    /* cloud.c:656-663 */
-    ieache_cloudkey *key = nullptr;
-    if ((rc = ieache_cloudkey_load_file(ctx, (d + "/cloud.key").c_str(), &key))) return rc;
-    std::unique_ptr<ieache_cloudkey, void (*)(ieache_cloudkey *)> key_guard(key, ieache_cloudkey_destroy);
-    HostKeySet nbit;
-    if ((rc = read_keyset((d + "/nbit.key").c_str(), nbit, false, msg))) return fail(rc, "%s", msg.c_str());
-    if (!nbit.has_secret) return fail(IEACHE_ERR_FORMAT, "nbit.key holds no secret key");
-    const int n = key->p.n, nb = nbit.p.n;
-    if (nb != n) return fail(IEACHE_ERR_UNSUPPORTED, "nbit.key and cloud.key use different n (%d vs %d)", nb, n);
-    const size_t w = n + 1, B = 32 * w;
+    ieache_session *sess = nullptr;
+    if ((rc = ieache_session_open(ctx, (d + "/cloud.key").c_str(), (d + "/nbit.key").c_str(), &sess))) return rc;
+    std::unique_ptr<ieache_session, void (*)(ieache_session *)> guard(sess, ieache_session_close);
+    const int n = sess->key->p.n;
+    const size_t w = n + 1;
     /* cloud.c:703-766: two client blocks of 11 x 32 samples */
     std::vector<int32_t> data(704 * w);
     {
@@ -789,61 +973,22 @@ extern "C" int ieache_cloud_run(ieache_ctx *ctx, const char *dir, double *second
         if (fscanf(f, "%d", &int_op) != 1) int_op = 0;
         fclose(f);
     }
-    const int32_t *neg1 = &data[0], *bit1 = &data[B], *carry1 = &data[10 * B], *neg2 = &data[11 * B], *bit2 = &data[12 * B];
-    const int32_t int_bit1 = dec32(nbit, bit1), int_bit2 = dec32(nbit, bit2);    /* cloud.c:709-746 */
-    int32_t n1 = dec32(nbit, neg1);
-    const int32_t n2 = dec32(nbit, neg2);                                        /* cloud.c:780-796 */
-    if (n1 == 2) n1 = 1;
-    const int32_t int_negative = n1 + n2;
-    const int32_t code = int_negative == 3 ? 4 : int_negative;                   /* cloud.c:812-821 */
     std::vector<int32_t> answer(352 * w);
-    enc32(nbit, code, &answer[0]);
-    int32_t int_bit;
-    if (int_op == 4) {                                                           /* cloud.c:833-843 */
-        int_bit = std::max(int_bit1, int_bit2);
-        enc32(nbit, int_bit * 2, &answer[B]);
-    } else if (int_bit1 >= int_bit2) { int_bit = int_bit1; memcpy(&answer[B], bit1, B * 4); }
-    else { int_bit = int_bit2; memcpy(&answer[B], bit2, B * 4); }
     size_t out_count = 64;
-    int exit_code = 0;
-    int kind = 0;
-    bool swap_ops = false;
-    if (int_op == 4 && int_bit >= 256) exit_code = 126;                          /* cloud.c:860-864 */
-    else if ((int_op == 1 && int_negative != 1 && int_negative != 2) || (int_op == 2 && (int_negative == 1 || int_negative == 2)))
-        kind = IEACHE_CIRC_ADD;                                                  /* cloud.c:870 */
-    else if (int_op == 2 || (int_op == 1 && (int_negative == 1 || int_negative == 2))) {
-        kind = IEACHE_CIRC_SUB;                                                  /* cloud.c:1194 */
-        swap_ops = !((int_op == 2 && int_negative == 0) || (int_op == 1 && int_negative == 2)); /* cloud.c:1196,1809 */
-    } else if (int_op == 4) kind = IEACHE_CIRC_MUL;                              /* cloud.c:2368 */
     double secs = 0;
-    if (kind) {
-        ieache_circuit *circ = nullptr;
-        if (ieache_circuit_build(kind, int_bit, &circ) == IEACHE_OK) {
-            std::unique_ptr<ieache_circuit, void (*)(ieache_circuit *)> cg(circ, ieache_circuit_destroy);
-            const int nc = int_bit / 32;
-            std::vector<int32_t> in((size_t)circ->c.n_inputs * w), out(circ->c.outputs.size() * w);
-            const int32_t *op1 = &data[2 * B], *op2 = &data[13 * B];
-            memcpy(&in[0], swap_ops ? op2 : op1, (size_t)nc * B * 4);
-            memcpy(&in[(size_t)nc * B], swap_ops ? op1 : op2, (size_t)nc * B * 4);
-            memcpy(&in[(size_t)2 * nc * B], carry1, B * 4);
-            const auto t0 = std::chrono::steady_clock::now();
-            if ((rc = ieache_circuit_eval(ctx, key, circ, in.data(), out.data(), 1))) return rc;
-            secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-            const size_t nres = circ->c.outputs.size() / 32;
-            for (size_t q = 0; q < 8; q++) memcpy(&answer[(2 + q) * B], q < nres ? &out[q * B] : carry1, B * 4);   /* cloud.c:899-916 */
-            memcpy(&answer[10 * B], carry1, B * 4);
-            out_count = 352;
-            printf("Computation Time: %lf[sec]\n", secs);                       /* cloud.c:896 */
-            if (kind == IEACHE_CIRC_MUL) {                                       /* cloud.c:2468-2471 */
-                FILE *t = fopen((d + "/averagestandard.txt").c_str(), "a");
-                if (t) { fprintf(t, "%lf\n", secs); fclose(t); }
-            }
+    const int exit_code = ieache_session_compute(sess, int_op, &data[0], &data[352 * w], answer.data(), &out_count, &secs);
+    if (exit_code < 0) return exit_code;
+    if (out_count == 352) {
+        printf("Computation Time: %lf[sec]\n", secs);                           /* cloud.c:896 */
+        if (int_op == 4) {                                                       /* cloud.c:2468-2471 */
+            FILE *t = fopen((d + "/averagestandard.txt").c_str(), "a");
+            if (t) { fprintf(t, "%lf\n", secs); fclose(t); }
         }
     }
     if (seconds) *seconds = secs;
     FILE *f = fopen((d + "/answer.data").c_str(), "wb");
     if (!f) return fail(IEACHE_ERR_IO, "cannot write %s/answer.data", dir);
-    rc = write_samples(f, n, answer.data(), out_count, key->p.ks_stdev * key->p.ks_stdev);
+    rc = write_samples(f, n, answer.data(), out_count, sess->key->p.ks_stdev * sess->key->p.ks_stdev);
     fclose(f);
     if (rc) return fail(rc, "short write on answer.data");
     return exit_code;

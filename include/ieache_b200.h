@@ -172,6 +172,27 @@ int ieache_circuit_eval_device(ieache_ctx *ctx, const ieache_cloudkey *key, cons
  * circuit time the reference prints as "Computation Time". */
 int ieache_cloud_run(ieache_ctx *ctx, const char *dir, double *seconds);
 
+/* ---- sessions: keys loaded once, operators chained in memory, requests batched ---- */
+typedef struct ieache_session ieache_session;
+/* loads cloud.key onto the GPU and the LWE key of nbit.key (Cloud/cloud.c:656-663) once */
+int ieache_session_open(ieache_ctx *ctx, const char *cloud_key_path, const char *nbit_key_path, ieache_session **out);
+/* same from objects already in memory; the cloud key is borrowed */
+int ieache_session_open_keys(ieache_ctx *ctx, ieache_cloudkey *key, const int32_t *nbit_lwe_key, ieache_session **out);
+void ieache_session_close(ieache_session *s);
+int ieache_session_params(const ieache_session *s, ieache_params *out);
+/* Cloud/cloud.c main() on memory blocks: operand blocks are the 352-sample client layout (11 x 32 samples,
+ * packed n+1 words); answer is 352 samples (64 on the abort path).  Returns 0 / 126 / negative error. */
+int ieache_session_compute(ieache_session *s, int op, const int32_t *operand1, const int32_t *operand2, int32_t *answer,
+                           size_t *answer_count, double *seconds);
+/* `count` independent requests; requests needing the same circuit share every level launch */
+int ieache_session_compute_batch(ieache_session *s, size_t count, const int32_t *ops, const int32_t *operands1,
+                                 const int32_t *operands2, int32_t *answers, int32_t *exit_codes, size_t *answer_counts,
+                                 double *seconds);
+/* whole postfix expressions ("AB*C+"), the walk of Cloud/dragonfly_cipher_cloud.py:685-729 without the
+ * answer.data -> cloud.data round trips; operands: [n_expr][n_operands][352][n+1] */
+int ieache_session_eval_postfix(ieache_session *s, const char *postfix, size_t n_expr, const int32_t *operands,
+                                int n_operands, int32_t *answers, size_t *answer_counts, double *seconds);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,113 @@
+"""GPU tests of the widened rows: sessions, in-memory chaining of operators for whole
+postfix expressions, and batched requests — against the oracle's cloud main() chained the way the reference
+chains it, and against Python integers."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_bind as ob
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env(pkg, oracle):
+    eng = pkg.Engine(0)
+    ks = oracle.keygen(ob.params_default(8), seed=31)
+    nbit = oracle.keygen(ob.params_default(8), seed=32)
+    key = eng.cloud_key_from_arrays(pkg.Params.default(8), ks.bk_coef(), ks.ksk())
+    sess = eng.session_from_keys(key, nbit.lwe_key())
+    yield eng, ks, nbit, sess
+    sess.close(); key.close(); ks.free(); nbit.free(); eng.close()
+
+
+def _signed(sign, v):
+    return -v if sign == 2 else v
+
+
+def test_session_compute_matches_oracle_main(oracle, env):
+    eng, ks, nbit, sess = env
+    for op, s1, s2, width, a, b in [(1, 0, 0, 32, 1 << 30, 1 << 30), (2, 0, 0, 32, 7, 1000), (4, 2, 0, 32, 77777, 99999),
+                                    (1, 2, 2, 64, 1 << 40, 12345)]:
+        A, B = oracle.alice(ks, nbit, s1, width, a, seed=1), oracle.alice(ks, nbit, s2, width, b, seed=2)
+        rc, ans, _ = sess.compute(op, A, B)
+        rc_o, ans_o = oracle.cloud_main(ks, nbit, op, np.concatenate([A, B]))
+        assert rc == rc_o == 0 and len(ans) == 352
+        assert oracle.verif(ks, nbit, ans) == oracle.verif(ks, nbit, ans_o)
+        code, w, chunks = oracle.verif(ks, nbit, ans)
+        assert ob.decode_result(op, code, w, chunks) == {1: lambda x, y: x + y, 2: lambda x, y: x - y, 4: lambda x, y: x * y}[op](
+            _signed(s1, a), _signed(s2, b))
+
+
+@pytest.mark.parametrize("postfix,fn", [("AB*C+", lambda a, b, c: a * b + c), ("ABC*+", lambda a, b, c: a + b * c),
+                                         ("AB+C+", lambda a, b, c: a + b + c), ("AB+C-", lambda a, b, c: a + b - c)])
+def test_postfix_chaining(oracle, env, postfix, fn):
+    """3-operand expressions (BASELINE.json config 3; the paper's A+B+C, A+B-C, A+B*C): the GPU session against
+    the oracle chained through memory the way dragonfly_cipher_cloud.py chains through files."""
+    eng, ks, nbit, sess = env
+    vals = [(123456, 7890, 4242), (1 << 30, 1 << 30, 1 << 30)]
+    ops = np.stack([np.stack([oracle.alice(ks, nbit, 0, 32, v, seed=10 * e + k) for k, v in enumerate(t)]) for e, t in enumerate(vals)])
+    rc, ans, counts, secs = sess.eval_postfix(postfix, ops)
+    assert rc == 0 and (counts == 352).all()
+    for e, t in enumerate(vals):
+        # oracle: same walk, operator by operator
+        stack = []
+        for tok in postfix:
+            if tok.isalpha():
+                stack.append(ops[e, ord(tok) - 65])
+            else:
+                y, x = stack.pop(), stack.pop()
+                _, r = oracle.cloud_main(ks, nbit, {"+": 1, "-": 2, "*": 4}[tok], np.concatenate([x, y]))
+                stack.append(r)
+        want = oracle.verif(ks, nbit, stack[-1])
+        got = oracle.verif(ks, nbit, ans[e])
+        assert got == want
+        code, w, chunks = got
+        last_op = {"+": 1, "-": 2, "*": 4}[postfix[-1]]
+        assert ob.decode_result(last_op, code, w, chunks) == fn(*t)
+
+
+def test_batched_requests_mixed_circuits(oracle, env):
+    """f-4: a batch of independent requests with different operators, signs and widths in one call"""
+    eng, ks, nbit, sess = env
+    reqs = [(1, 0, 0, 32, 11, 22), (2, 0, 0, 32, 100, 1), (1, 0, 0, 32, 5, 6), (4, 0, 0, 32, 300, 400), (2, 0, 2, 32, 9, 3),
+            (1, 0, 0, 64, 1 << 35, 7), (2, 0, 0, 32, 3, 100), (4, 0, 0, 256, 1, 1)]
+    o1 = np.stack([oracle.alice(ks, nbit, r[1], r[3], r[4], seed=2 * i) for i, r in enumerate(reqs)])
+    o2 = np.stack([oracle.alice(ks, nbit, r[2], r[3], r[5], seed=2 * i + 1) for i, r in enumerate(reqs)])
+    codes, ans, counts, _ = sess.compute_batch([r[0] for r in reqs], o1, o2)
+    for i, (op, s1, s2, width, a, b) in enumerate(reqs):
+        if op == 4 and width == 256:
+            assert codes[i] == 126 and counts[i] == 64          # Cloud/cloud.c:860-864
+            continue
+        assert codes[i] == 0 and counts[i] == 352
+        code, w, chunks = oracle.verif(ks, nbit, ans[i])
+        want = {1: _signed(s1, a) + _signed(s2, b), 2: _signed(s1, a) - _signed(s2, b), 4: _signed(s1, a) * _signed(s2, b)}[op]
+        assert ob.decode_result(op, code, w, chunks) == want, i
+
+
+def test_cloud_dynamic_mirror(tmp_path, pkg, oracle, env):
+    """the ctypes replacement for dragonfly_cipher_cloud.py's compute()/compute_final() on the reference's files"""
+    eng, ks, nbit, _ = env
+    from ieache_b200 import cloud_dynamic as cd
+    d = str(tmp_path)
+    ks.write_cloud_key(os.path.join(d, "cloud.key"))
+    nbit.write_secret_key(os.path.join(d, "nbit.key"))
+    files = []
+    for k, v in enumerate((1000, 2000, 3000)):
+        p = os.path.join(d, f"client{k}.data")
+        ks.write_samples(oracle.alice(ks, nbit, 0, 32, v, seed=k), p)
+        files.append(p)
+    node = cd.CloudNode(d, engine=eng)
+    # compute(): operator on cloud.data = client0 || client1
+    blk = np.concatenate([cd.read_block(files[0], 8), cd.read_block(files[1], 8)])
+    cd.write_block(os.path.join(d, "cloud.data"), blk, node.variance)
+    assert os.path.getsize(os.path.join(d, "cloud.data")) == 704 * (4 + 4 * 9 + 8)
+    assert node.compute(1) == 0
+    code, w, chunks = oracle.verif(ks, nbit, ks.read_samples(os.path.join(d, "answer.data"), 352))
+    assert (code, w, chunks[0]) == (0, 32, 3000)
+    # evaluate(): A*B+C
+    assert node.evaluate("AB*C+", files) == 0
+    code, w, chunks = oracle.verif(ks, nbit, ks.read_samples(os.path.join(d, "answer.data"), 352))
+    assert w == 64 and chunks[0] | (chunks[1] << 32) == 1000 * 2000 + 3000
+    node.close()
