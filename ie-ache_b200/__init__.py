@@ -108,6 +108,10 @@ def lib() -> ctypes.CDLL:
     L.ieache_session_compute.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, POINTER(c_size_t), POINTER(c_double)]
     L.ieache_session_compute_batch.argtypes = [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_double)]
     L.ieache_session_eval_postfix.argtypes = [c_void_p, c_char_p, c_size_t, c_void_p, c_int, c_void_p, c_void_p, POINTER(c_double)]
+    L.ieache_keygen_files.argtypes = [c_void_p, c_char_p, POINTER(Params), c_uint64, c_uint64]
+    L.ieache_alice_encrypt.argtypes = [c_char_p, c_int32, c_int32, c_void_p, c_char_p, c_int]
+    L.ieache_alice_run.argtypes = [c_char_p]
+    L.ieache_verif_run.argtypes = [c_char_p, c_char_p, c_size_t, POINTER(c_int32), POINTER(c_int32)]
     L.ieache_keygen.argtypes = [c_void_p, POINTER(Params), c_uint64, POINTER(c_void_p), POINTER(c_void_p), c_void_p, c_void_p]
     L.ieache_secretkey_import.argtypes = [c_void_p, POINTER(Params), c_void_p, c_void_p, POINTER(c_void_p)]
     L.ieache_secretkey_export.argtypes = [c_void_p, c_void_p, c_void_p]
@@ -116,6 +120,25 @@ def lib() -> ctypes.CDLL:
     L.ieache_sym_decrypt_device.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]
     _lib = L
     return L
+
+
+def alice_encrypt(directory: str, sign_code: int, width: int, value: int, out_path: str, append: bool = False) -> None:
+    """Client1/alice.c: one operand of `width` bits -> 352 ciphertext records (needs secret.key, nbit.key in directory)"""
+    chunks = np.array([(value >> (32 * i)) & 0xFFFFFFFF for i in range(8)], dtype=np.uint32)
+    _check(lib().ieache_alice_encrypt(directory.encode(), sign_code, width, _ptr(chunks), out_path.encode(), int(append)))
+
+
+def alice_run(directory: str) -> None:
+    """./alice: values.txt -> cloud.data"""
+    _check(lib().ieache_alice_run(directory.encode()))
+
+
+def verif_run(directory: str):
+    """./verif: answer.data + operator.txt -> (decimal value, sign code, width)"""
+    buf = ctypes.create_string_buffer(128)
+    sc, w = c_int32(), c_int32()
+    _check(lib().ieache_verif_run(directory.encode(), buf, 128, byref(sc), byref(w)))
+    return int(buf.value.decode()), sc.value, w.value
 
 
 def set_wide_max(max_gates: int) -> int:
@@ -373,6 +396,10 @@ class Engine:
 
     def eval_device(self, key: CloudKey, circ: Circuit, in_dev: int, out_dev: int, n_expr: int):
         _check(lib().ieache_circuit_eval_device(self._h, key._h, circ._h, c_void_p(in_dev), c_void_p(out_dev), n_expr))
+
+    def keygen_files(self, directory: str, params: Params | None = None, seed_key: int = 314_1592_657, seed_nbit: int = 314_1592_888):
+        """Keygen/keygen.c: secret.key, cloud.key, nbit.key (the default seeds echo the reference's seed triples)"""
+        _check(lib().ieache_keygen_files(self._h, directory.encode(), byref(params) if params is not None else None, seed_key, seed_nbit))
 
     def session(self, cloud_key_path: str, nbit_key_path: str) -> Session:
         h = c_void_p()

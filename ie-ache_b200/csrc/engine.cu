@@ -993,3 +993,169 @@ extern "C" int ieache_cloud_run(ieache_ctx *ctx, const char *dir, double *second
     if (rc) return fail(rc, "short write on answer.data");
     return exit_code;
 }
+
+/* ------------------------------------------------------------------ the callers on either side of the path
+ * (SURVEY.md §8 f-2, f-3): Keygen/keygen.c, Client1/alice.c, Output/verif.c on the reference's files. */
+
+/* Keygen/keygen.c:22-51: two independent secret key sets (main key: seed {314,1592,657}; nbit key: seed
+ * {314,1592,888} in the reference); writes secret.key, cloud.key, nbit.key.  Keys are generated on the GPU. */
+extern "C" int ieache_keygen_files(ieache_ctx *ctx, const char *dir, const ieache_params *p, uint64_t seed_key, uint64_t seed_nbit)
+{
+    if (!ctx || !dir) return fail(IEACHE_ERR_ARG, "null argument");
+    ieache_params def{};
+    if (!p) {
+        def.n = 630; def.N = 1024; def.k = 1; def.bk_l = 3; def.bk_Bgbit = 7; def.ks_t = 8; def.ks_basebit = 2;
+        def.ks_stdev = 1.0 / 32768.0; def.bk_stdev = 1.0 / 33554432.0; def.max_stdev = 0.012467;
+        p = &def;
+    }
+    int rc = check_params(p);
+    if (rc) return rc;
+    const std::string d(dir);
+    const size_t bk_words = (size_t)p->n * 2 * p->bk_l * 2 * 1024, ks_words = (size_t)1024 * p->ks_t * (1u << p->ks_basebit) * (p->n + 1);
+    for (int which = 0; which < 2; which++) {
+        HostKeySet hk;
+        hk.p = *p; hk.bk.resize(bk_words); hk.ksk.resize(ks_words);
+        hk.lwe_key.resize(p->n); hk.tlwe_key.resize(1024); hk.has_secret = true;
+        ieache_secretkey *sk = nullptr;
+        ieache_cloudkey *ck = nullptr;
+        if ((rc = ieache_keygen(ctx, p, which ? seed_nbit : seed_key, &sk, &ck, hk.bk.data(), hk.ksk.data()))) return rc;
+        ieache_secretkey_export(sk, hk.lwe_key.data(), hk.tlwe_key.data());
+        ieache_secretkey_destroy(sk);
+        ieache_cloudkey_destroy(ck);
+        std::string msg;
+        if (which == 0) {
+            if ((rc = write_keyset((d + "/secret.key").c_str(), hk, true, msg))) return fail(rc, "%s", msg.c_str());   /* keygen.c:39-41 */
+            if ((rc = write_keyset((d + "/cloud.key").c_str(), hk, false, msg))) return fail(rc, "%s", msg.c_str());   /* keygen.c:44-46 */
+        } else if ((rc = write_keyset((d + "/nbit.key").c_str(), hk, true, msg))) return fail(rc, "%s", msg.c_str());  /* keygen.c:49-51 */
+    }
+    return IEACHE_OK;
+}
+
+/* Client1/alice.c:116-189: sign code and width under the nbit key, 8 value chunks (least significant first)
+ * and a zero carry block under the main key -> 352 samples appended to or written at out_path */
+extern "C" int ieache_alice_encrypt(const char *dir, int32_t sign_code, int32_t width, const uint32_t *chunks, const char *out_path,
+                                    int append)
+{
+    if (!dir || !chunks || !out_path) return fail(IEACHE_ERR_ARG, "null argument");
+    const std::string d(dir);
+    HostKeySet key, nbit;
+    std::string msg;
+    int rc;
+    if ((rc = read_keyset((d + "/secret.key").c_str(), key, false, msg))) return fail(rc, "%s", msg.c_str());   /* alice.c:36-38 */
+    if ((rc = read_keyset((d + "/nbit.key").c_str(), nbit, false, msg))) return fail(rc, "%s", msg.c_str());    /* alice.c:40-42 */
+    if (!key.has_secret || !nbit.has_secret) return fail(IEACHE_ERR_FORMAT, "secret.key / nbit.key hold no secret key");
+    const int n = key.p.n;
+    if (nbit.p.n != n) return fail(IEACHE_ERR_UNSUPPORTED, "secret.key and nbit.key use different n");
+    const size_t w = n + 1, B = 32 * w;
+    std::vector<int32_t> blk(352 * w);
+    enc32(nbit, sign_code, &blk[0]);
+    enc32(nbit, width, &blk[B]);
+    for (int c = 0; c < 8; c++) enc32(key, c < width / 32 ? (int32_t)chunks[c] : 0, &blk[(2 + c) * B]);   /* unused chunks: plaintext3 = 0 */
+    enc32(key, 0, &blk[10 * B]);
+    FILE *f = fopen(out_path, append ? "ab" : "wb");
+    if (!f) return fail(IEACHE_ERR_IO, "cannot write %s", out_path);
+    rc = write_samples(f, n, blk.data(), 352, key.p.ks_stdev * key.p.ks_stdev);
+    fclose(f);
+    return rc ? fail(rc, "short write on %s", out_path) : IEACHE_OK;
+}
+
+/* Client1/alice.c main(): values.txt (lines of 32 binary digits: sign code, bit count, chunks) -> cloud.data */
+extern "C" int ieache_alice_run(const char *dir)
+{
+    if (!dir) return fail(IEACHE_ERR_ARG, "null argument");
+    const std::string d(dir);
+    FILE *f = fopen((d + "/values.txt").c_str(), "r");
+    if (!f) return fail(IEACHE_ERR_IO, "cannot open %s/values.txt", dir);
+    char line[128];
+    std::vector<uint32_t> vals;
+    while (fgets(line, sizeof line, f)) {
+        uint32_t v = 0;
+        int digits = 0;
+        for (const char *c = line; *c == '0' || *c == '1'; ++c, ++digits) v = (v << 1) | (uint32_t)(*c - '0');
+        if (digits) vals.push_back(v);
+    }
+    fclose(f);
+    if (vals.size() < 3) return fail(IEACHE_ERR_FORMAT, "values.txt: expected sign code, bit count and chunks");
+    uint32_t chunks[8] = {0};
+    for (size_t i = 2; i < vals.size() && i < 10; i++) chunks[i - 2] = vals[i];
+    return ieache_alice_encrypt(dir, (int32_t)vals[0], (int32_t)vals[1], chunks, (d + "/cloud.data").c_str(), 0);
+}
+
+static std::string u256_to_decimal(const uint32_t *limbs_le, int nlimbs, bool negative)
+{
+    std::vector<uint32_t> v(limbs_le, limbs_le + nlimbs);
+    std::string out;
+    bool nonzero = false;
+    for (uint32_t x : v) nonzero |= x != 0;
+    if (!nonzero) return "0";
+    while (true) {
+        bool any = false;
+        uint64_t rem = 0;
+        for (int i = nlimbs - 1; i >= 0; i--) {
+            const uint64_t cur = (rem << 32) | v[i];
+            v[i] = (uint32_t)(cur / 1000000000u);
+            rem = cur % 1000000000u;
+            any |= v[i] != 0;
+        }
+        char buf[16];
+        snprintf(buf, sizeof buf, any ? "%09u" : "%u", (unsigned)rem);
+        out = std::string(buf) + out;
+        if (!any) break;
+    }
+    return negative ? "-" + out : out;
+}
+
+/* Output/verif.c: decrypt answer.data (sign code and width under the nbit key, width/32 chunks under the main
+ * key, :46-95), reassemble chunks most significant first (:229) and apply the sign rules of each operator
+ * (:120-173 add, :733-789 subtract, :1409-1435 multiply).  result receives the decimal string verif prints. */
+extern "C" int ieache_verif_run(const char *dir, char *result, size_t result_cap, int32_t *sign_code, int32_t *width)
+{
+    if (!dir) return fail(IEACHE_ERR_ARG, "null argument");
+    const std::string d(dir);
+    HostKeySet key, nbit;
+    std::string msg;
+    int rc;
+    if ((rc = read_keyset((d + "/secret.key").c_str(), key, false, msg))) return fail(rc, "%s", msg.c_str());   /* verif.c:22-24 */
+    if ((rc = read_keyset((d + "/nbit.key").c_str(), nbit, false, msg))) return fail(rc, "%s", msg.c_str());    /* verif.c:27-29 */
+    if (!key.has_secret || !nbit.has_secret) return fail(IEACHE_ERR_FORMAT, "secret.key / nbit.key hold no secret key");
+    const int n = key.p.n;
+    const size_t w = n + 1, B = 32 * w;
+    int int_op = 0;
+    {
+        FILE *f = fopen((d + "/operator.txt").c_str(), "r");                     /* verif.c:66-69 */
+        if (!f) return fail(IEACHE_ERR_IO, "cannot open %s/operator.txt", dir);
+        if (fscanf(f, "%d", &int_op) != 1) int_op = 0;
+        fclose(f);
+    }
+    std::vector<int32_t> ans(352 * w);
+    FILE *f = fopen((d + "/answer.data").c_str(), "rb");
+    if (!f) return fail(IEACHE_ERR_IO, "cannot open %s/answer.data", dir);
+    rc = read_samples(f, n, ans.data(), 64);
+    if (rc) { fclose(f); return fail(rc, "answer.data: short read"); }
+    const int32_t code = dec32(nbit, &ans[0]), bits = dec32(nbit, &ans[B]);
+    if (sign_code) *sign_code = code;
+    if (width) *width = bits;
+    const int nchunks = bits / 32;
+    if (nchunks < 1 || nchunks > 8) { fclose(f); return fail(IEACHE_ERR_FORMAT, "answer.data: implausible width %d", bits); }
+    rc = read_samples(f, n, &ans[2 * B], (size_t)nchunks * 32);
+    fclose(f);
+    if (rc) return fail(rc, "answer.data holds no result chunks (abort path of Cloud/cloud.c:860-864?)");
+    uint32_t limbs[9] = {0};
+    for (int c = 0; c < nchunks; c++) limbs[c] = (uint32_t)dec32(key, &ans[(2 + c) * B]);
+    /* two's-complement reinterpretation happens only for 32-character strings (verif.c:148,747) */
+    bool negative = false;
+    const bool twos = bits == 32 && (limbs[0] >> 31);
+    auto negate32 = [&]() { limbs[0] = (uint32_t)(-(int32_t)limbs[0]); negative = !negative; };
+    if (int_op == 1) {
+        if (code != 0 && code != 4 && twos) negate32();
+        if (code == 4) negative = !negative;
+    } else if (int_op == 2) {
+        if (code != 2 && twos) negate32();
+        if (code == 1) negative = !negative;
+    } else if (int_op == 4) {
+        negative = (code == 1 || code == 2);
+    } else return fail(IEACHE_ERR_ARG, "operator.txt holds %d", int_op);
+    const std::string dec = u256_to_decimal(limbs, 8, negative);
+    if (result && result_cap) snprintf(result, result_cap, "%s", dec.c_str());
+    return IEACHE_OK;
+}

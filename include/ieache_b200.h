@@ -172,6 +172,17 @@ int ieache_circuit_eval_device(ieache_ctx *ctx, const ieache_cloudkey *key, cons
  * circuit time the reference prints as "Computation Time". */
 int ieache_cloud_run(ieache_ctx *ctx, const char *dir, double *seconds);
 
+/* ---- the callers on either side of the path, on the reference's files ---- */
+/* Keygen/keygen.c: writes secret.key, cloud.key, nbit.key into dir (p == NULL: lambda = 110 defaults) */
+int ieache_keygen_files(ieache_ctx *ctx, const char *dir, const ieache_params *p, uint64_t seed_key, uint64_t seed_nbit);
+/* Client1/alice.c: one operand (sign code 0/2, width, 8 chunks least significant first) -> 352 records */
+int ieache_alice_encrypt(const char *dir, int32_t sign_code, int32_t width, const uint32_t *chunks, const char *out_path,
+                         int append);
+int ieache_alice_run(const char *dir); /* values.txt -> cloud.data, like ./alice */
+/* Output/verif.c: decrypts answer.data with secret.key / nbit.key, applies the sign rules of operator.txt and
+ * returns the decimal string verif prints */
+int ieache_verif_run(const char *dir, char *result, size_t result_cap, int32_t *sign_code, int32_t *width);
+
 /* ---- sessions: keys loaded once, operators chained in memory, requests batched ---- */
 typedef struct ieache_session ieache_session;
 /* loads cloud.key onto the GPU and the LWE key of nbit.key (Cloud/cloud.c:656-663) once */
