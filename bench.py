@@ -145,6 +145,7 @@ def main():
     ap.add_argument("--log2-gates", type=int, default=20, help="gates per step and per GPU (default 2^20, BASELINE.json config 2)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-expression", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -258,7 +259,7 @@ def main():
     # memory view: BK streamed once per launch (reuse across all gates of the launch) + per-gate inputs/outputs
     alg_bytes = BK_BYTES + gates_per_launch * (2 * 2524 + 4100)
     roofline = {
-        "kernel": "blind_rotate_kernel<L=3,G=1,MINB=4>", "bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+        "kernel": "blind_rotate_kernel<L=3,G=1,MINB=4,ROLL=2>", "bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
         "frac": achieved_tflops / fp64_peak if fp64_peak else None, "traffic": traffic,
         "peak_source": "dense FP64 FMA microbenchmark run live by this bench (MEASURED_PEAKS.json has no FP64 figure)",
         "flop_per_gate": FLOP_PER_BOOTSTRAP, "gates_per_launch": gates_per_launch, "ms_per_launch": br_ms,
@@ -309,6 +310,40 @@ def main():
         e2e = {"value": world * count * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 2 * count * n1 * 4,
                "d2h_bytes_per_step": count * n1 * 4, "api": "ieache_gate_batch (C ABI, pinned host buffers)"}
 
+    # ---- 3-operand expression latency (BASELINE.json metric, config 3), rank 0 at N = 1 only -----------
+    expression = None
+    if rank == 0 and world == 1 and not args.skip_expression:
+        circ = eng.circuit(m.CIRC_MULADD, 32)        # a*b+c: mul32 then 64-bit add, 11 584 bootstraps, 257 levels
+        def run_expr(n_expr, reps):
+            rng2 = np.random.default_rng(99)
+            vals = rng2.integers(0, 2 ** 31, size=(n_expr, 5), dtype=np.int64)
+            vals[:, 3:] = 0                           # high chunk of c and the carry block are encryptions of 0
+            ebits = ((vals[:, :, None] >> np.arange(32)) & 1).astype(np.int32).reshape(-1)
+            d_in = eng.device_alloc(ebits.size * m.DEVICE_STRIDE * 4)
+            d_res = eng.device_alloc(n_expr * circ.n_outputs * m.DEVICE_STRIDE * 4)
+            sk.encrypt_to_device(ebits, d_in, seed=77)
+            times = []
+            for r in range(reps + 1):
+                eng.sync(); t0 = time.perf_counter()
+                eng.eval_device(key, circ, d_in, d_res, n_expr); eng.sync()
+                if r:
+                    times.append(time.perf_counter() - t0)
+            ob_ = sk.decrypt_from_device(d_res, n_expr * circ.n_outputs).reshape(n_expr, 2, 32).astype(np.int64)
+            words = (ob_ << np.arange(32)).sum(axis=2)
+            good = all(int(words[e, 0]) | (int(words[e, 1]) << 32) == int(vals[e, 0]) * int(vals[e, 1]) + int(vals[e, 2]) for e in range(n_expr))
+            eng.device_free(d_in); eng.device_free(d_res)
+            if not good:
+                raise SystemExit("a*b+c: wrong decrypted result")
+            return float(np.median(times))
+        lat = run_expr(1, 3)
+        nb = 64
+        tb = run_expr(nb, 1)
+        expression = {"workload": "a*b+c on 32-bit operands: mul32 then 64-bit add (Cloud/cloud.c circuits), 11584 bootstraps, 257 levels",
+                      "latency_ms": 1e3 * lat, "batch": {"n_expr": nb, "seconds": tb, "gates_per_s": nb * circ.bootstraps / tb,
+                                                          "ms_per_expression": 1e3 * tb / nb},
+                      "reference_paper": "A+B*C 329 s on a single-core i7 VM (AC058.pdf p.4, whole run, other hardware)",
+                      "verified": "decrypted results equal a*b+c"}
+
     # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1:
@@ -325,7 +360,7 @@ def main():
                        "params": "n=630,N=1024,k=1,l=3,Bgbit=7,t=8,basebit=2", "parallelism": f"dp{world} (key replicated, no data-path collective)",
                        "l2": f"inputs {2 * count * 2528 / 1e9:.1f} GB per GPU, larger than L2 (126 MB); no flush needed",
                        "key_broadcast_ms": t_bcast_ms, "verified": f"{len(sub)} decrypted results per rank against the NAND truth table"},
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "expression": expression,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

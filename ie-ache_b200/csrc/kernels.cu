@@ -111,13 +111,13 @@ constexpr int kAbarBytes = 2080;
 constexpr int kGroupSmem = kAccBytes + 2 * kBufBytes + kAbarBytes; /* 28704 */
 
 /* L = gadget length, G = gates (64-thread groups) per CTA, MINB = CTAs per SM the register
- * allocation is tuned for, ROLL = keep the (k+1)l forward transforms in a rolled loop so the
+ * allocation is tuned for, ROLL = 0 unrolled step body, 1 rolled over both loops, 2 rolled over digits only, 3 over polynomials only: the
  * step body fits the 32 KB instruction cache (the fully unrolled body is ~60 KB of SASS) */
-template <int L, int G, int MINB, bool ROLL, bool NOBK = false, bool LOCK = false>
+template <int L, int G, int MINB, int ROLL, bool NOBK = false, bool LOCK = false>
 __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
                     const int32_t *__restrict__ baseB, int32_t *__restrict__ ext);
 
-template <int L, int G, int MINB, bool ROLL, bool NOBK = false, bool LOCK = false>
+template <int L, int G, int MINB, int ROLL, bool NOBK = false, bool LOCK = false>
 __global__ void __launch_bounds__(64 * G, MINB)
 blind_rotate_kernel(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
                     const int32_t *__restrict__ baseB, int32_t *__restrict__ ext)
@@ -130,10 +130,10 @@ __global__ void __maxnreg__(200)
 blind_rotate_kernel_r200(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
                          const int32_t *__restrict__ baseB, int32_t *__restrict__ ext)
 {
-    blind_rotate_body<L, 1, 5, false, false, false>(p, bkfft, ga, baseA, baseB, ext);
+    blind_rotate_body<L, 1, 5, 0, false, false>(p, bkfft, ga, baseA, baseB, ext);
 }
 
-template <int L, int G, int MINB, bool ROLL, bool NOBK, bool LOCK>
+template <int L, int G, int MINB, int ROLL, bool NOBK, bool LOCK>
 __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
                     const int32_t *__restrict__ baseB, int32_t *__restrict__ ext)
 {
@@ -207,11 +207,11 @@ __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__
         for (int r = 0; r < 8; r++) { s0r[r] = 0.0; s0i[r] = 0.0; s1r[r] = 0.0; s1i[r] = 0.0; }
         const double2 *bk_r = bkfft + (size_t)i * kBkStride + tid;
 
-#pragma unroll(ROLL ? 1 : 2)
+#pragma unroll((ROLL == 1 || ROLL == 3) ? 1 : 2)
         for (int q = 0; q < 2; q++) {
             int32_t c[16];
             rot_minus_one(acc + q * kN, tid, a, c);
-#pragma unroll(ROLL ? 1 : L)
+#pragma unroll((ROLL == 1 || ROLL == 2) ? 1 : L)
             for (int pp = 0; pp < L; pp++) {
                 const int shift = 32 - (pp + 1) * Bgbit;
                 double xr[8], xi[8];
@@ -234,7 +234,7 @@ __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__
             }
         }
         /* inverse transforms and ACC update; the second pass reuses the code of the first */
-#pragma unroll(ROLL ? 1 : 2)
+#pragma unroll((ROLL != 0) ? 1 : 2)
         for (int j = 0; j < 2; j++) {
             cd *buf = toggle ? bufB : bufA;
             toggle ^= 1;
@@ -510,13 +510,13 @@ static cudaError_t launch_br_wide(const DevParams &p, const double2 *bkfft, cons
 static int br_variant()
 {
     static int v = -1;
-    if (v < 0) { const char *e = getenv("IEACHE_BR_VARIANT"); v = e ? atoi(e) : 7; }
+    if (v < 0) { const char *e = getenv("IEACHE_BR_VARIANT"); v = e ? atoi(e) : 23; }
     return v;
 }
 int blind_rotate_groups_per_cta() { const int v = br_variant(); return (v == 4 || v == 11 || v == 13) ? 4 : ((v == 0 || v == 1 || v == 3 || v == 5 || v == 6 || v == 12) ? 2 : 1); }
 int blind_rotate_smem_bytes(int groups) { return groups * kGroupSmem; }
 
-template <int L, int G, int MINB, bool ROLL, bool NOBK = false, bool LOCK = false>
+template <int L, int G, int MINB, int ROLL, bool NOBK = false, bool LOCK = false>
 static cudaError_t launch_br_variant(const DevParams &p, const double2 *bkfft, const GateAddr &ga, const int32_t *baseA,
                                      const int32_t *baseB, int32_t *ext, long long count, cudaStream_t s)
 {
@@ -545,33 +545,37 @@ cudaError_t launch_blind_rotate(const DevParams &p, const double2 *bkfft, const 
             if (p.l == 2) return launch_br_pair<2>(p, bkfft, ga, baseA, baseB, ext, count, s);
         }
     }
-    if (p.l == 2) return launch_br_variant<2, 1, 4, false>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    if (p.l == 2) return launch_br_variant<2, 1, 4, 2>(p, bkfft, ga, baseA, baseB, ext, count, s);
     if (p.l != 3) return cudaErrorInvalidValue;
     switch (br_variant()) {
-    case 0: return launch_br_variant<3, 2, 2, false>(p, bkfft, ga, baseA, baseB, ext, count, s); /* round-1 first version */
-    case 2: return launch_br_variant<3, 1, 6, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 3: return launch_br_variant<3, 2, 2, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 4: return launch_br_variant<3, 4, 1, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 5: return launch_br_variant<3, 2, 4, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 6: return launch_br_variant<3, 2, 3, false>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 8: return launch_br_variant<3, 1, 5, false>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 9: return launch_br_variant<3, 1, 6, false>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 10: return launch_br_variant<3, 1, 5, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 0: return launch_br_variant<3, 2, 2, 0>(p, bkfft, ga, baseA, baseB, ext, count, s); /* round-1 first version */
+    case 2: return launch_br_variant<3, 1, 6, 1>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 3: return launch_br_variant<3, 2, 2, 1>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 4: return launch_br_variant<3, 4, 1, 1>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 5: return launch_br_variant<3, 2, 4, 1>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 6: return launch_br_variant<3, 2, 3, 0>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 8: return launch_br_variant<3, 1, 5, 0>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 9: return launch_br_variant<3, 1, 6, 0>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 10: return launch_br_variant<3, 1, 5, 1>(p, bkfft, ga, baseA, baseB, ext, count, s);
     case 20: {
         cudaError_t e = cudaFuncSetAttribute(blind_rotate_kernel_r200<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGroupSmem);
         if (e != cudaSuccess) return e;
         blind_rotate_kernel_r200<3><<<(int)count, 64, kGroupSmem, s>>>(p, bkfft, ga, baseA, baseB, ext);
         return cudaGetLastError();
     }
-    case 11: return launch_br_variant<3, 4, 1, false, false, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 12: return launch_br_variant<3, 2, 2, false, false, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 13: return launch_br_variant<3, 4, 1, false, false, false>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 21: return launch_br_variant<3, 1, 6, 2>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 22: return launch_br_variant<3, 1, 6, 3>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 24: return launch_br_variant<3, 1, 4, 3>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 11: return launch_br_variant<3, 4, 1, 0, false, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 12: return launch_br_variant<3, 2, 2, 0, false, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 13: return launch_br_variant<3, 4, 1, 0, false, false>(p, bkfft, ga, baseA, baseB, ext, count, s);
     /* timing experiments only (wrong results): no BK loads */
-    case 107: return launch_br_variant<3, 1, 4, false, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 109: return launch_br_variant<3, 1, 6, false, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 102: return launch_br_variant<3, 1, 6, true, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 1: return launch_br_variant<3, 2, 3, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    default: return launch_br_variant<3, 1, 4, false>(p, bkfft, ga, baseA, baseB, ext, count, s); /* 7: best measured */
+    case 107: return launch_br_variant<3, 1, 4, 0, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 109: return launch_br_variant<3, 1, 6, 0, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 102: return launch_br_variant<3, 1, 6, 1, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 1: return launch_br_variant<3, 2, 3, 1>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 7: return launch_br_variant<3, 1, 4, 0>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    default: return launch_br_variant<3, 1, 4, 2>(p, bkfft, ga, baseA, baseB, ext, count, s); /* 23: as fast as the fully unrolled body (7) at half the code size */
     }
 }
 

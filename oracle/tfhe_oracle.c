@@ -108,6 +108,7 @@ typedef struct {
     int N, M;          /* M = N/2 complex points */
     double *tw_re, *tw_im;   /* psi^j, j<M, psi = exp(i*pi/N) */
     double *w_re, *w_im;     /* exp(+2*pi*i*j/M), j<M/2 */
+    double *st_re, *st_im;   /* per-stage contiguous twiddles for len = 8, 16, ..., M */
     int *rev;
 } FftCtx;
 
@@ -132,6 +133,8 @@ static const FftCtx *fft_ctx(int N)
             c->rev = (int *)malloc(sizeof(int) * M);
             for (int j = 0; j < M; j++) { c->tw_re[j] = cos(M_PI * j / N); c->tw_im[j] = sin(M_PI * j / N); }
             for (int j = 0; j < M / 2; j++) { c->w_re[j] = cos(2.0 * M_PI * j / M); c->w_im[j] = sin(2.0 * M_PI * j / M); }
+            c->st_re = (double *)malloc(sizeof(double) * M); c->st_im = (double *)malloc(sizeof(double) * M);
+            { int off = 0; for (int len = 8; len <= M; len <<= 1) { int half = len >> 1; for (int j = 0; j < half; j++) { c->st_re[off + j] = cos(2.0 * M_PI * j / len); c->st_im[off + j] = sin(2.0 * M_PI * j / len); } off += half; } }
             int lg = 0; while ((1 << lg) < M) lg++;
             for (int j = 0; j < M; j++) { int r = 0; for (int b = 0; b < lg; b++) if (j & (1 << b)) r |= 1 << (lg - 1 - b); c->rev[j] = r; }
             g_nctx++;
@@ -141,22 +144,39 @@ static const FftCtx *fft_ctx(int N)
     return ret;
 }
 
-/* in-place radix-2 DIT on bit-reversed input; sign = +1 uses exp(+2 pi i jk/M) */
-static void cfft(const FftCtx *c, double *re, double *im, int sign)
+/* in-place radix-2 DIT on bit-reversed input; sign = +1 uses exp(+2 pi i jk/M).
+ * Twiddles of every stage are stored contiguously (st_re/st_im) so the inner loop vectorises (AVX2 via
+ * -march=x86-64-v3): this is the CPU baseline of bench.py, it should not be needlessly slow. */
+static void cfft(const FftCtx *c, double *restrict re, double *restrict im, int sign)
 {
-    int M = c->M;
-    for (int len = 2; len <= M; len <<= 1) {
-        int half = len >> 1, step = M / len;
+    const int M = c->M;
+    /* first two stages (half = 1, 2) without multiplications by non-trivial twiddles */
+    for (int base = 0; base < M; base += 2) {
+        double ur = re[base], ui = im[base], xr = re[base + 1], xi = im[base + 1];
+        re[base] = ur + xr; im[base] = ui + xi; re[base + 1] = ur - xr; im[base + 1] = ui - xi;
+    }
+    for (int base = 0; base < M; base += 4) {
+        double ur = re[base], ui = im[base], xr = re[base + 2], xi = im[base + 2];
+        re[base] = ur + xr; im[base] = ui + xi; re[base + 2] = ur - xr; im[base + 2] = ui - xi;
+        /* twiddle exp(sign * i pi/2) = sign * i */
+        ur = re[base + 1]; ui = im[base + 1]; xr = -sign * im[base + 3]; xi = sign * re[base + 3];
+        re[base + 1] = ur + xr; im[base + 1] = ui + xi; re[base + 3] = ur - xr; im[base + 3] = ui - xi;
+    }
+    int off = 0;
+    for (int len = 8; len <= M; len <<= 1) {
+        const int half = len >> 1;
+        const double *restrict wr = c->st_re + off, *restrict wi0 = c->st_im + off;
         for (int base = 0; base < M; base += len) {
+            double *restrict ar = re + base, *restrict ai = im + base, *restrict br = re + base + half, *restrict bi = im + base + half;
             for (int j = 0; j < half; j++) {
-                double wr = c->w_re[j * step], wi = sign * c->w_im[j * step];
-                double xr = re[base + j + half], xi = im[base + j + half];
-                double tr = xr * wr - xi * wi, ti = xr * wi + xi * wr;
-                double ur = re[base + j], ui = im[base + j];
-                re[base + j] = ur + tr; im[base + j] = ui + ti;
-                re[base + j + half] = ur - tr; im[base + j + half] = ui - ti;
+                const double wi = sign * wi0[j];
+                const double tr = br[j] * wr[j] - bi[j] * wi, ti = br[j] * wi + bi[j] * wr[j];
+                const double ur = ar[j], ui = ai[j];
+                ar[j] = ur + tr; ai[j] = ui + ti;
+                br[j] = ur - tr; bi[j] = ui - ti;
             }
         }
+        off += half;
     }
 }
 /* real coefficients p[0..N) -> M evaluations at psi^(4k+1) (libtfhe "LagrangeHalfC") */
