@@ -74,6 +74,10 @@ void gate(int op, LweSample *result, const LweSample *a, const LweSample *b, con
     const CloudWrap *w = cw(bk);
     const int n = w->params->raw.n;
     const size_t rec = (size_t)n + 1;
+    /* cloud.c calls gates from OpenMP sections on a shared key (cloud.c:27-41): the engine context's staging
+     * buffers are not shared between concurrent calls, so calls are serialised here */
+    static std::mutex gate_mu;
+    std::lock_guard<std::mutex> lk(gate_mu);
     std::vector<int32_t> buf(4 * rec * count);
     int32_t *pa = buf.data(), *pb = pa + rec * count, *pc = pb + rec * count, *po = pc + rec * count;
     for (int32_t g = 0; g < count; g++) {
