@@ -46,9 +46,11 @@ cudaError_t twiddle_ptrs(const Tw **tw2, const Tw **tw3)
 /* named barrier of one 64-thread group.  With one group per CTA the id is a compile-time constant (ptxas then
  * reserves 2 barriers instead of 16, worth ~5 % in the throughput kernel); a switch over immediate ids was
  * measured slower than the register form for the multi-group kernels. */
+constexpr int kCtaBarrier = -1; /* group id meaning "the gate's threads are spread over every warp of the CTA" */
 __device__ __forceinline__ void group_sync(int grp)
 {
-    asm volatile("bar.sync %0, 64;" ::"r"(grp + 1) : "memory");
+    if (grp < 0) __syncthreads();
+    else asm volatile("bar.sync %0, 64;" ::"r"(grp + 1) : "memory");
 }
 
 /* forward transform of the 8 points in registers; leaves evaluations in x[r] of thread t3 = tid */
@@ -113,16 +115,16 @@ constexpr int kGroupSmem = kAccBytes + 2 * kBufBytes + kAbarBytes; /* 28704 */
 /* L = gadget length, G = gates (64-thread groups) per CTA, MINB = CTAs per SM the register
  * allocation is tuned for, ROLL = 0 unrolled step body, 1 rolled over both loops, 2 rolled over digits only, 3 over polynomials only: the
  * step body fits the 32 KB instruction cache (the fully unrolled body is ~60 KB of SASS) */
-template <int L, int G, int MINB, int ROLL, bool NOBK = false, bool LOCK = false>
+template <int L, int G, int MINB, int ROLL, bool NOBK = false, bool LOCK = false, bool SPREAD = false>
 __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
                     const int32_t *__restrict__ baseB, int32_t *__restrict__ ext);
 
-template <int L, int G, int MINB, int ROLL, bool NOBK = false, bool LOCK = false>
+template <int L, int G, int MINB, int ROLL, bool NOBK = false, bool LOCK = false, bool SPREAD = false>
 __global__ void __launch_bounds__(64 * G, MINB)
 blind_rotate_kernel(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
                     const int32_t *__restrict__ baseB, int32_t *__restrict__ ext)
 {
-    blind_rotate_body<L, G, MINB, ROLL, NOBK, LOCK>(p, bkfft, ga, baseA, baseB, ext);
+    blind_rotate_body<L, G, MINB, ROLL, NOBK, LOCK, SPREAD>(p, bkfft, ga, baseA, baseB, ext);
 }
 /* same body with an explicit register cap (5 CTAs of 64 threads per SM at 200 registers) */
 template <int L>
@@ -133,12 +135,20 @@ blind_rotate_kernel_r200(DevParams p, const double2 *__restrict__ bkfft, GateAdd
     blind_rotate_body<L, 1, 5, 0, false, false>(p, bkfft, ga, baseA, baseB, ext);
 }
 
-template <int L, int G, int MINB, int ROLL, bool NOBK, bool LOCK>
+template <int L, int G, int MINB, int ROLL, bool NOBK, bool LOCK, bool SPREAD>
 __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
                     const int32_t *__restrict__ baseB, int32_t *__restrict__ ext)
 {
+    static_assert(!SPREAD || (LOCK && (G == 2 || G == 4)), "SPREAD: 2 or 4 lock-step gates per CTA");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int grp = (G == 1) ? 0 : (threadIdx.x >> 6), tid = (G == 1) ? threadIdx.x : (threadIdx.x & 63);
+    /* SPREAD: every warp holds 32/G lanes of each of the CTA's G gates (gate thread tid = warp * 32/G + lane % (32/G)),
+     * so the lanes of different gates that own the same transform slots read the same BK_i addresses in the same
+     * instruction: one 128-byte wavefront serves G gates (784 -> 784/G LSU wavefronts per gate-step for BK, and
+     * 1/G of the L2->L1 traffic).  The price: the G gates run in lock step on CTA-wide barriers. */
+    constexpr int LPG = 32 / (SPREAD ? G : 1);
+    const int grp = SPREAD ? (int)((threadIdx.x & 31) / LPG) : ((G == 1) ? 0 : (threadIdx.x >> 6));
+    const int tid = SPREAD ? (int)((threadIdx.x >> 5) * LPG + (threadIdx.x & (LPG - 1))) : ((G == 1) ? threadIdx.x : (threadIdx.x & 63));
+    const int bar = SPREAD ? kCtaBarrier : grp; /* barrier domain of one transform */
     int g = blockIdx.x * G + grp;
     const bool active = g < ga.ntempl * ga.n_inst;
     if (!LOCK && !active) return; /* whole group leaves; groups never share a barrier */
@@ -167,7 +177,7 @@ __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__
             abar[i] = (uint16_t)modswitch_2N(v);
         }
     }
-    group_sync(grp);
+    group_sync(bar);
     /* 2. ACC = (0, X^{2N-bbar} * mu * (1 + X + ... + X^{N-1})) */
     {
         const int bbar = abar[n];
@@ -179,7 +189,7 @@ __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__
             acc[kN + j] = ((j < ar) != flip) ? -p.mu : p.mu;
         }
     }
-    group_sync(grp);
+    group_sync(bar);
 
     const Tw w1 = tw_pass1();
     const Tw w2 = d_tw2[tid >> 3];
@@ -199,9 +209,11 @@ __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__
     for (int i = 0; i < n; i++) {
         /* LOCK: all gates of the CTA enter step i together, so BK_i is fetched from L2 once per CTA and the
          * other groups hit it in L1 */
-        if (LOCK) __syncthreads();
+        if (LOCK && !SPREAD) __syncthreads();
         const int a = abar[i];
-        if (a == 0) continue; /* uniform inside the group */
+        /* a = 0 adds exactly zero (all digits of (X^0 - 1) ACC are 0); the skip is only a shortcut, and the gates
+         * of a SPREAD CTA share barriers, so they all run the step */
+        if (!SPREAD && a == 0) continue; /* uniform inside the group */
         double s0r[8], s0i[8], s1r[8], s1i[8];
 #pragma unroll
         for (int r = 0; r < 8; r++) { s0r[r] = 0.0; s0i[r] = 0.0; s1r[r] = 0.0; s1i[r] = 0.0; }
@@ -222,7 +234,7 @@ __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__
                 }
                 cd *buf = toggle ? bufB : bufA;
                 toggle ^= 1;
-                fwd_transform(xr, xi, buf, tid, grp, w1, w2, w3);
+                fwd_transform(xr, xi, buf, tid, bar, w1, w2, w3);
 #pragma unroll
                 for (int r = 0; r < 8; r++) {
                     const double2 b0 = NOBK ? make_double2(1.0 + r, 0.5) : __ldg(bk_r + r * 64);
@@ -238,7 +250,7 @@ __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__
         for (int j = 0; j < 2; j++) {
             cd *buf = toggle ? bufB : bufA;
             toggle ^= 1;
-            inv_transform(s0r, s0i, buf, tid, grp, w1, w2, w3);
+            inv_transform(s0r, s0i, buf, tid, bar, w1, w2, w3);
             int32_t *accj = acc + j * kN;
 #pragma unroll
             for (int m = 0; m < 8; m++) {
@@ -248,7 +260,7 @@ __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__
 #pragma unroll
             for (int r = 0; r < 8; r++) { s0r[r] = s1r[r]; s0i[r] = s1i[r]; }
         }
-        group_sync(grp);
+        group_sync(bar);
     }
 
     /* 4. SampleExtract at index 0 */
@@ -446,13 +458,16 @@ blind_rotate_pair_kernel(DevParams p, const double2 *__restrict__ bkfft, GateAdd
             }
             cd *buf = toggle ? bufB : bufA;
             toggle ^= 1;
+            /* the row's 16 KB of BK_i are requested before the transform: with one gate per SM nothing else hides
+             * the L2 latency (the barriers inside the transform keep the compiler from sinking the loads) */
+            double2 b0[8], b1[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) { b0[r] = __ldg(bk_mine + pp * kRowElems + r * 64); b1[r] = __ldg(bk_other + pp * kRowElems + r * 64); }
             fwd_transform(xr, xi, buf, tid, grp, w1, w2, w3);
 #pragma unroll
             for (int r = 0; r < 8; r++) {
-                const double2 b0 = __ldg(bk_mine + pp * kRowElems + r * 64);
-                const double2 b1 = __ldg(bk_other + pp * kRowElems + r * 64);
-                cmac(mr[r], mi[r], xr[r], xi[r], b0.x, b0.y);
-                cmac(orr[r], oi[r], xr[r], xi[r], b1.x, b1.y);
+                cmac(mr[r], mi[r], xr[r], xi[r], b0[r].x, b0[r].y);
+                cmac(orr[r], oi[r], xr[r], xi[r], b1[r].x, b1[r].y);
             }
         }
         /* hand the other polynomial's partial sum over */
@@ -513,18 +528,18 @@ static int br_variant()
     if (v < 0) { const char *e = getenv("IEACHE_BR_VARIANT"); v = e ? atoi(e) : 23; }
     return v;
 }
-int blind_rotate_groups_per_cta() { const int v = br_variant(); return (v == 4 || v == 11 || v == 13) ? 4 : ((v == 0 || v == 1 || v == 3 || v == 5 || v == 6 || v == 12) ? 2 : 1); }
+int blind_rotate_groups_per_cta() { const int v = br_variant(); return (v == 4 || v == 11 || v == 13 || v == 31 || v == 34) ? 4 : ((v == 0 || v == 1 || v == 3 || v == 5 || v == 6 || v == 12 || v == 30 || v == 32 || v == 33) ? 2 : 1); }
 int blind_rotate_smem_bytes(int groups) { return groups * kGroupSmem; }
 
-template <int L, int G, int MINB, int ROLL, bool NOBK = false, bool LOCK = false>
+template <int L, int G, int MINB, int ROLL, bool NOBK = false, bool LOCK = false, bool SPREAD = false>
 static cudaError_t launch_br_variant(const DevParams &p, const double2 *bkfft, const GateAddr &ga, const int32_t *baseA,
                                      const int32_t *baseB, int32_t *ext, long long count, cudaStream_t s)
 {
     const int smem = G * kGroupSmem;
     const int grid = (int)((count + G - 1) / G);
-    cudaError_t e = cudaFuncSetAttribute(blind_rotate_kernel<L, G, MINB, ROLL, NOBK, LOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(blind_rotate_kernel<L, G, MINB, ROLL, NOBK, LOCK, SPREAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    blind_rotate_kernel<L, G, MINB, ROLL, NOBK, LOCK><<<grid, 64 * G, smem, s>>>(p, bkfft, ga, baseA, baseB, ext);
+    blind_rotate_kernel<L, G, MINB, ROLL, NOBK, LOCK, SPREAD><<<grid, 64 * G, smem, s>>>(p, bkfft, ga, baseA, baseB, ext);
     return cudaGetLastError();
 }
 
@@ -566,6 +581,12 @@ cudaError_t launch_blind_rotate(const DevParams &p, const double2 *bkfft, const 
     case 21: return launch_br_variant<3, 1, 6, 2>(p, bkfft, ga, baseA, baseB, ext, count, s);
     case 22: return launch_br_variant<3, 1, 6, 3>(p, bkfft, ga, baseA, baseB, ext, count, s);
     case 24: return launch_br_variant<3, 1, 4, 3>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    /* SPREAD: lanes of 2 / 4 gates interleaved in every warp (shared BK_i wavefronts) */
+    case 30: return launch_br_variant<3, 2, 2, 2, false, true, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 31: return launch_br_variant<3, 4, 1, 2, false, true, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 32: return launch_br_variant<3, 2, 3, 2, false, true, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 33: return launch_br_variant<3, 2, 2, 0, false, true, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 34: return launch_br_variant<3, 4, 1, 0, false, true, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
     case 11: return launch_br_variant<3, 4, 1, 0, false, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
     case 12: return launch_br_variant<3, 2, 2, 0, false, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
     case 13: return launch_br_variant<3, 4, 1, 0, false, false>(p, bkfft, ga, baseA, baseB, ext, count, s);
