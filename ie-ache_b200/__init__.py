@@ -96,6 +96,8 @@ def lib() -> ctypes.CDLL:
     L.ieache_cloud_run.argtypes = [c_void_p, c_char_p, POINTER(c_double)]
     L.ieache_set_wide_max.restype = ctypes.c_int64
     L.ieache_set_wide_max.argtypes = [ctypes.c_int64]
+    L.ieache_set_cluster_max.restype = ctypes.c_int64
+    L.ieache_set_cluster_max.argtypes = [ctypes.c_int64]
     L.ieache_ctx_timer_start.argtypes = [c_void_p]
     L.ieache_ctx_timer_stop.argtypes = [c_void_p, POINTER(c_double)]
     L.ieache_measure_fp64_peak.argtypes = [c_void_p, POINTER(c_double)]
@@ -144,6 +146,11 @@ def verif_run(directory: str):
 def set_wide_max(max_gates: int) -> int:
     """Launches of <= max_gates gates use the latency kernel; returns the previous threshold."""
     return lib().ieache_set_wide_max(max_gates)
+
+
+def set_cluster_max(max_gates: int) -> int:
+    """Launches of <= max_gates gates use the 2-SM cluster latency kernel; returns the previous threshold."""
+    return lib().ieache_set_cluster_max(max_gates)
 
 
 def _check(rc: int) -> None:

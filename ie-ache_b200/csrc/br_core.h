@@ -156,15 +156,15 @@ IE_HD void ld_ipass1(const cd *buf, int tid, double (&xr)[8], double (&xi)[8])
 /* c[m] = coefficient tid+64m, c[8+m] = coefficient tid+64m+512 of (X^a - 1) * acc, 0 < a < 2N */
 IE_HD void rot_minus_one(const int32_t *acc /*1024*/, int tid, int a, int32_t (&c)[16])
 {
-    const int ar = a & (kN - 1);
-    const bool flip = a >= kN;
+    /* j - a lies in (-2N, N): its low 10 bits are the source index and bit 10 says whether the term picked up a sign
+     * from X^N = -1 (once for a borrow, once more for a >= N) */
+    const int t0 = tid - a;
 #pragma unroll
     for (int h = 0; h < 16; h++) {
-        const int j = tid + 64 * (h & 7) + 512 * (h >> 3);
-        const int src = (j - ar) & (kN - 1);
-        int32_t v = acc[src];
-        const bool neg = (j < ar) != flip;
-        c[h] = (neg ? -v : v) - acc[j];
+        const int off = 64 * (h & 7) + 512 * (h >> 3);
+        const int t = t0 + off;
+        const int32_t v = acc[t & (kN - 1)];
+        c[h] = ((t & kN) ? -v : v) - acc[tid + off];
     }
 }
 /* digit p of the signed base-2^Bgbit decomposition (tGswTorus32PolynomialDecompH) */
@@ -172,6 +172,19 @@ IE_HD double digit_f64(int32_t c, uint32_t offset, int shift, uint32_t mask, int
 {
     const uint32_t v = (uint32_t)c + offset;
     return (double)((int32_t)((v >> shift) & mask) - halfBg);
+}
+
+/* same value built without the int->double conversion unit: 2^52 + u has u in its low mantissa word, and the
+ * subtraction is exact.  One FP64 add instead of an XU-pipe I2F (8 issue cycles per warp): used where a single
+ * gate's latency matters; the throughput kernel keeps I2F because its FP64 pipe is the scarce one. */
+IE_HD double digit_f64_magic(int32_t c, uint32_t offset, int shift, uint32_t mask, int32_t halfBg)
+{
+    const uint32_t u = (((uint32_t)c + offset) >> shift) & mask;
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(0x43300000, (int)u) - (4503599627370496.0 + (double)halfBg);
+#else
+    return (double)((int32_t)u - halfBg);
+#endif
 }
 
 /* round a double (|v| < 2^51) to the nearest integer and keep the low 32 bits */

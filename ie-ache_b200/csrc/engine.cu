@@ -165,6 +165,12 @@ extern "C" int64_t ieache_set_wide_max(int64_t max_gates)
     if (max_gates >= 0) set_wide_max(max_gates);
     return old;
 }
+extern "C" int64_t ieache_set_cluster_max(int64_t max_gates)
+{
+    const long long old = get_cluster_max();
+    if (max_gates >= 0) set_cluster_max(max_gates);
+    return old;
+}
 extern "C" int ieache_ctx_timer_start(ieache_ctx *ctx)
 {
     if (!ctx) return fail(IEACHE_ERR_ARG, "null ctx");

@@ -21,6 +21,7 @@
 #include <cooperative_groups.h>
 #include <math.h>
 #include <stdlib.h>
+#include <stdio.h>
 
 namespace ieache {
 
@@ -82,6 +83,14 @@ __device__ __forceinline__ void inv_transform(double (&xr)[8], double (&xi)[8], 
     pass_inv(xr, xi, w1);
 }
 
+/* read-only 16-byte load whose position in the instruction stream is pinned (volatile): the compiler would
+ * otherwise hoist BK_i requests to the top of a step, in front of the ACC reads the transform is waiting for */
+__device__ __forceinline__ double2 ldg_pinned(const double2 *p)
+{
+    double2 v;
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
 /* ------------------------------------------------------------------ key load */
 __global__ void __launch_bounds__(64) bk_fft_kernel(const int32_t *__restrict__ coef, double2 *__restrict__ out, int npoly)
 {
@@ -493,6 +502,228 @@ blind_rotate_pair_kernel(DevParams p, const double2 *__restrict__ bkfft, GateAdd
     if (threadIdx.x == 0) o[kN] = acc[kN];
 }
 
+/* ---- latency variant on a 2-CTA cluster: one gate on two SMs ----
+ * CTA q of the pair owns ACC polynomial q (decomposition input q and CMux output q).  Its l groups run the l
+ * forward transforms of that polynomial's digits at the same time and multiply by their BK_i rows for both output
+ * polynomials.  Each group parks its product for polynomial q in local shared memory and sends its product for
+ * polynomial 1-q to the peer CTA with one 8 KB bulk copy (shared::cta -> shared::cluster, completion counted on
+ * the peer's mbarrier); group 0 then adds the l local and the l received products, inverts and updates ACC_q.
+ * Critical path per step: one forward and one inverse transform (the two-group kernel above has l + 1), at the
+ * cost of two SMs per gate: a circuit level of one expression (<= 54 gates for a*b+c) fits the 74
+ * cluster slots of a B200 in one wave.
+ * Measured while building this (B200, cycles per step): 512 separate 16-byte remote stores + release-arrive, or
+ * st.async, or a pre-summed single bulk copy all delivered ~1200 cycles after the send; mbarrier.try_wait on the
+ * receiving side added ~500 cycles over a test_wait poll. */
+constexpr int kClPartialBytes = kHalfN * 16; /* one partial product: 512 complex */
+__host__ __device__ constexpr int cluster_smem_bytes(int L)
+{
+    return kN * 4 + (L + 1) * kBufBytes + L * kClPartialBytes /*mine*/ + 2 * L * kClPartialBytes /*other, by parity*/ +
+           2 * L * kClPartialBytes /*received, by parity*/ + kAbarBytes + 64;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t map_to_peer(uint32_t local_addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int L, bool PROF = false>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 * L, 1)
+blind_rotate_cluster_kernel(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
+                            const int32_t *__restrict__ baseB, int32_t *__restrict__ ext)
+{
+    constexpr int NT = 64 * L;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int grp = threadIdx.x >> 6, tid = threadIdx.x & 63;
+    const int g = blockIdx.x >> 1;
+    uint32_t q;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(q));
+    int32_t *acc = reinterpret_cast<int32_t *>(smem_raw);                                  /* ACC_q */
+    cd *fbuf = reinterpret_cast<cd *>(smem_raw + kN * 4) + (size_t)grp * kBufElems;        /* forward exchange, per group */
+    cd *ibuf = reinterpret_cast<cd *>(smem_raw + kN * 4) + (size_t)L * kBufElems;          /* inverse exchange (group 0) */
+    cd *pmine = reinterpret_cast<cd *>(smem_raw + kN * 4 + (L + 1) * kBufBytes);           /* [L][512] products for polynomial q */
+    cd *pother = pmine + (size_t)L * kHalfN;                                               /* [2][L][512] products for polynomial 1-q: bulk-copy sources */
+    cd *recv = pother + (size_t)2 * L * kHalfN;                                            /* [2][L][512] written by the peer */
+    uint16_t *abar = reinterpret_cast<uint16_t *>(recv + (size_t)2 * L * kHalfN);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + cluster_smem_bytes(L) - 64);  /* [2], one per step parity */
+    constexpr uint32_t kStepTx = (uint32_t)L * kClPartialBytes;                            /* bytes the peer sends per step */
+
+    const int n = p.n;
+    if (threadIdx.x == 0) {
+        /* one local arrival per use, which also announces the bytes the peer's l bulk copies will deliver */
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar + 1)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(kStepTx) : "memory"); /* step 0 */
+    }
+    {
+        const int e = g / ga.ntempl, t = g - e * ga.ntempl;
+        GateT gt = ga.uni;
+        if (ga.tmpl) gt = ga.tmpl[t]; else { gt.in0 = (gt.in0 >= 0) ? t : -1; gt.in1 = (gt.in1 >= 0) ? t : -1; }
+        const size_t blk = (size_t)e * ga.inst_samples;
+        const int32_t *in0 = gt.in0 >= 0 ? baseA + (blk + gt.in0) * ga.stride : nullptr;
+        const int32_t *in1 = gt.in1 >= 0 ? baseB + (blk + gt.in1) * ga.stride : nullptr;
+        const int32_t c0 = gt.c0, c1 = gt.c1, cst = gt.cst_mu * p.mu;
+        for (int i = threadIdx.x; i <= n; i += NT) {
+            int32_t v = (i == n) ? cst : 0;
+            if (in0) v += c0 * __ldg(in0 + i);
+            if (in1) v += c1 * __ldg(in1 + i);
+            abar[i] = (uint16_t)modswitch_2N(v);
+        }
+    }
+    __syncthreads();
+    {
+        const int bbar = abar[n];
+        const int a = (2 * kN - bbar) & (2 * kN - 1), ar = a & (kN - 1);
+        const bool flip = a >= kN;
+        for (int j = threadIdx.x; j < kN; j += NT) acc[j] = (q == 0) ? 0 : (((j < ar) != flip) ? -p.mu : p.mu);
+    }
+    cluster_sync_all(); /* both CTAs' mbarriers are initialised and armed before anyone copies into the peer */
+
+    const Tw w1 = tw_pass1(), w2 = d_tw2[tid >> 3], w3 = d_tw3[tid];
+    const int Bgbit = p.Bgbit;
+    const uint32_t maskBg = (1u << Bgbit) - 1;
+    const int32_t halfBg = 1 << (Bgbit - 1);
+    uint32_t offset = 0;
+#pragma unroll
+    for (int i = 1; i <= L; i++) offset += (uint32_t)halfBg << (32 - i * Bgbit);
+    const int shift = 32 - (grp + 1) * Bgbit;
+    constexpr int kRowElems = 2 * kHalfN, kBkStride = 2 * L * kRowElems;
+    const uint32_t peer = q ^ 1u;
+    const uint32_t peer_recv = map_to_peer(smem_u32(recv), peer), peer_mbar = map_to_peer(smem_u32(mbar), peer);
+
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = 0;
+#define CL_TICK(k) do { if (PROF) { const long long tn = clock64(); tacc[k] += tn - tprev; tprev = tn; } } while (0)
+    int a = abar[0];
+    /* BK_i rows of this group (16 KB) live in registers and are requested one step ahead, right after the products
+     * of the current step have left: the LSU takes ~7 cycles per 512-byte global load, ~700 cycles per SM and step,
+     * which then overlap the wait for the peer instead of sitting in front of the transform */
+    double2 bm[8], bo[8];
+    {
+        const double2 *bk_r = bkfft + ((size_t)q * L + grp) * kRowElems + tid;
+#pragma unroll
+        for (int r = 0; r < 8; r++) { bm[r] = ldg_pinned(bk_r + q * kHalfN + r * 64); bo[r] = ldg_pinned(bk_r + (1 - q) * kHalfN + r * 64); }
+    }
+    for (int i = 0; i < n; i++) {
+        if (PROF) tprev = clock64();
+        const int par = i & 1;
+        /* arm the other barrier for step i+1: the peer cannot send that step's products before this CTA has sent
+         * step i's, which happens after this point in program order of thread 0's group */
+        if (threadIdx.x == 0 && i + 1 < n)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar + (par ^ 1))), "r"(kStepTx) : "memory");
+        double mr[8], mi[8];
+        {
+            double orr[8], oi[8];
+            int32_t c[16];
+            rot_minus_one(acc, tid, a, c); /* a = 0 gives all-zero digits: the step adds exactly zero, and the pair stays in step */
+            a = abar[i + 1];               /* abar has n + 1 entries; the value is only used by the next step */
+            CL_TICK(0);
+            double xr[8], xi[8];
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                xr[m] = digit_f64_magic(c[m], offset, shift, maskBg, halfBg);
+                xi[m] = digit_f64_magic(c[8 + m], offset, shift, maskBg, halfBg);
+            }
+            CL_TICK(1);
+            fwd_transform(xr, xi, fbuf, tid, grp, w1, w2, w3);
+            CL_TICK(2);
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                mr[r] = xr[r] * bm[r].x - xi[r] * bm[r].y; mi[r] = fma(xr[r], bm[r].y, xi[r] * bm[r].x);
+                orr[r] = xr[r] * bo[r].x - xi[r] * bo[r].y; oi[r] = fma(xr[r], bo[r].y, xi[r] * bo[r].x);
+            }
+            /* the product for the peer's polynomial leaves first: park, make it visible to the async proxy, one
+             * thread starts the copy once the whole group has parked */
+            cd *po = pother + ((size_t)par * L + grp) * kHalfN;
+#pragma unroll
+            for (int r = 0; r < 8; r++) { cd v; v.x = orr[r]; v.y = oi[r]; po[r * 64 + tid] = v; }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            group_sync(grp);
+            if (tid == 0)
+                asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(peer_recv + (uint32_t)(par * L + grp) * kClPartialBytes), "r"(smem_u32(po)), "r"(kClPartialBytes),
+                               "r"(peer_mbar + (uint32_t)par * 8u) : "memory");
+            if (grp != 0) {
+                cd *o = pmine + (size_t)grp * kHalfN + tid;
+#pragma unroll
+                for (int r = 0; r < 8; r++) { cd v; v.x = mr[r]; v.y = mi[r]; o[r * 64] = v; }
+            }
+            if (i + 1 < n) {
+                const double2 *bk_r = bkfft + (size_t)(i + 1) * kBkStride + ((size_t)q * L + grp) * kRowElems + tid;
+#pragma unroll
+                for (int r = 0; r < 8; r++) { bm[r] = ldg_pinned(bk_r + q * kHalfN + r * 64); bo[r] = ldg_pinned(bk_r + (1 - q) * kHalfN + r * 64); }
+            }
+        }
+        CL_TICK(3);
+        __syncthreads();
+        if (grp == 0) {
+#pragma unroll
+            for (int gg = 1; gg < L; gg++) {
+                const cd *in = pmine + (size_t)gg * kHalfN + tid;
+#pragma unroll
+                for (int r = 0; r < 8; r++) { const cd v = in[r * 64]; mr[r] += v.x; mi[r] += v.y; }
+            }
+            CL_TICK(4);
+            /* the peer's products of this step: mbar[par] is used every other step.  test_wait poll: try_wait's
+             * suspend was measured ~500 cycles slower here */
+            const uint32_t mb = smem_u32(mbar + par), phase = (uint32_t)(i >> 1) & 1u;
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(mb), "r"(phase) : "memory");
+            CL_TICK(5);
+#pragma unroll
+            for (int gg = 0; gg < L; gg++) {
+                const cd *in = recv + ((size_t)par * L + gg) * kHalfN + tid;
+#pragma unroll
+                for (int r = 0; r < 8; r++) { const cd v = in[r * 64]; mr[r] += v.x; mi[r] += v.y; }
+            }
+            inv_transform(mr, mi, ibuf, tid, 0, w1, w2, w3);
+            CL_TICK(6);
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                acc[tid + 64 * m] += round_to_torus(mr[m]);
+                acc[tid + 64 * m + 512] += round_to_torus(mi[m]);
+            }
+            CL_TICK(7);
+        }
+        __syncthreads();
+    }
+#undef CL_TICK
+    if (PROF && blockIdx.x < 2 && tid == 0)
+        printf("cluster prof cta %d grp %d cycles/step: bk+rot %lld digits %lld fwd %lld mac+send %lld localsum %lld wait %lld add+inv %lld update %lld\n",
+               (int)blockIdx.x, grp, tacc[0] / n, tacc[1] / n, tacc[2] / n, tacc[3] / n, tacc[4] / n, tacc[5] / n, tacc[6] / n, tacc[7] / n);
+    /* SampleExtract: the mask comes from ACC_0, the body from ACC_1[0] */
+    int32_t *o = ext + (size_t)g * kExtStride;
+    if (q == 0) { for (int j = threadIdx.x; j < kN; j += NT) o[j] = (j == 0) ? acc[0] : -acc[kN - j]; }
+    else if (threadIdx.x == 0) o[kN] = acc[0];
+    cluster_sync_all(); /* nobody leaves while the peer could still be copying into this CTA */
+}
+
+template <int L>
+static cudaError_t launch_br_cluster(const DevParams &p, const double2 *bkfft, const GateAddr &ga, const int32_t *baseA,
+                                     const int32_t *baseB, int32_t *ext, long long count, cudaStream_t s)
+{
+    constexpr int smem = cluster_smem_bytes(L);
+    static const bool prof = getenv("IEACHE_CLUSTER_PROF") != nullptr; /* developer aid: per-phase cycle counts of cluster 0 */
+    if (prof) {
+        cudaError_t e = cudaFuncSetAttribute(blind_rotate_cluster_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        blind_rotate_cluster_kernel<L, true><<<(int)count * 2, 64 * L, smem, s>>>(p, bkfft, ga, baseA, baseB, ext);
+        return cudaGetLastError();
+    }
+    cudaError_t e = cudaFuncSetAttribute(blind_rotate_cluster_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    blind_rotate_cluster_kernel<L><<<(int)count * 2, 64 * L, smem, s>>>(p, bkfft, ga, baseA, baseB, ext);
+    return cudaGetLastError();
+}
+
 template <int L>
 static cudaError_t launch_br_pair(const DevParams &p, const double2 *bkfft, const GateAddr &ga, const int32_t *baseA,
                                   const int32_t *baseB, int32_t *ext, long long count, cudaStream_t s)
@@ -509,6 +740,10 @@ static cudaError_t launch_br_pair(const DevParams &p, const double2 *bkfft, cons
 static long long g_wide_max = [] { const char *e = getenv("IEACHE_WIDE_MAX"); return e ? atoll(e) : 296LL; }();
 void set_wide_max(long long v) { g_wide_max = v; }
 long long get_wide_max() { return g_wide_max; }
+/* launches of at most this many gates use the 2-CTA-cluster kernel: 74 pairs of SMs run in one wave */
+static long long g_cluster_max = [] { const char *e = getenv("IEACHE_CLUSTER_MAX"); return e ? atoll(e) : 74LL; }();
+void set_cluster_max(long long v) { g_cluster_max = v; }
+long long get_cluster_max() { return g_cluster_max; }
 
 template <int L>
 static cudaError_t launch_br_wide(const DevParams &p, const double2 *bkfft, const GateAddr &ga, const int32_t *baseA,
@@ -550,6 +785,10 @@ cudaError_t launch_blind_rotate(const DevParams &p, const double2 *bkfft, const 
     if (count <= 0) return cudaSuccess;
     ext += (size_t)ext_base * kExtStride;
     /* narrow launches (a circuit level of a few expressions): per-gate latency is what matters */
+    if (count <= g_cluster_max && count <= g_wide_max) {
+        if (p.l == 3) return launch_br_cluster<3>(p, bkfft, ga, baseA, baseB, ext, count, s);
+        if (p.l == 2) return launch_br_cluster<2>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    }
     if (count <= g_wide_max) {
         static const int lat = [] { const char *e = getenv("IEACHE_LATENCY_KERNEL"); return e ? atoi(e) : 2; }();
         if (lat == 6) {

@@ -79,6 +79,9 @@ cudaError_t launch_fp64_peak(cudaStream_t s, double *tflops);
 /* launches with <= wide_max gates use the latency kernel (one gate per CTA, 2l groups) */
 void set_wide_max(long long v);
 long long get_wide_max();
+/* launches with <= cluster_max gates (and <= wide_max) use the 2-CTA-cluster latency kernel (one gate on two SMs) */
+void set_cluster_max(long long v);
+long long get_cluster_max();
 
 int blind_rotate_smem_bytes(int groups);
 int blind_rotate_groups_per_cta();

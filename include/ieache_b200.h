@@ -70,6 +70,10 @@ int ieache_ctx_set_timing(ieache_ctx *ctx, int enabled);
  * (one gate per CTA, one thread group per forward transform), larger ones the throughput variant.
  * Process-wide; returns the previous value; a negative argument only queries.  Default 296 (two waves of one-gate CTAs on 148 SMs). */
 int64_t ieache_set_wide_max(int64_t max_gates);
+/* Launches of at most max_gates gates (and at most the limit above) use the cluster latency kernel: one gate on a
+ * pair of SMs (thread-block cluster of 2, products exchanged through distributed shared memory).  Same calling
+ * convention as ieache_set_wide_max.  Default 74 (148 SMs / 2: one wave). */
+int64_t ieache_set_cluster_max(int64_t max_gates);
 /* step timer: CUDA events on the engine's stream (torch events only see torch's stream) */
 int ieache_ctx_timer_start(ieache_ctx *ctx);
 int ieache_ctx_timer_stop(ieache_ctx *ctx, double *elapsed_ms); /* records, synchronises, returns the elapsed device time */

@@ -52,12 +52,15 @@ def small(pkg, oracle, eng):
     key.close(); ks.free(); nbit.free()
 
 
-@pytest.fixture(params=["latency_kernel", "throughput_kernel"])
+@pytest.fixture(params=["cluster_kernel", "pair_kernel", "throughput_kernel"])
 def kernel_mode(pkg, request):
-    """both blind-rotation kernels must pass the same parity tests whatever the launch size"""
-    old = pkg.set_wide_max(1 << 40 if request.param == "latency_kernel" else 0)
+    """the three blind-rotation kernels (one gate on a 2-SM cluster / on two groups of one SM / one group per
+    gate) must pass the same parity tests whatever the launch size"""
+    old = pkg.set_wide_max(0 if request.param == "throughput_kernel" else 1 << 40)
+    oldc = pkg.set_cluster_max(1 << 40 if request.param == "cluster_kernel" else 0)
     yield request.param
     pkg.set_wide_max(old)
+    pkg.set_cluster_max(oldc)
 
 
 # ------------------------------------------------------------------ gates
