@@ -462,8 +462,8 @@ blind_rotate_pair_kernel(DevParams p, const double2 *__restrict__ bkfft, GateAdd
             double xr[8], xi[8];
 #pragma unroll
             for (int m = 0; m < 8; m++) {
-                xr[m] = digit_f64(c[m], offset, shift, maskBg, halfBg);
-                xi[m] = digit_f64(c[8 + m], offset, shift, maskBg, halfBg);
+                xr[m] = digit_f64_magic(c[m], offset, shift, maskBg, halfBg);
+                xi[m] = digit_f64_magic(c[8 + m], offset, shift, maskBg, halfBg);
             }
             cd *buf = toggle ? bufB : bufA;
             toggle ^= 1;
