@@ -98,6 +98,8 @@ def lib() -> ctypes.CDLL:
     L.ieache_set_wide_max.argtypes = [ctypes.c_int64]
     L.ieache_set_cluster_max.restype = ctypes.c_int64
     L.ieache_set_cluster_max.argtypes = [ctypes.c_int64]
+    L.ieache_set_ks_staged_min.restype = ctypes.c_int64
+    L.ieache_set_ks_staged_min.argtypes = [ctypes.c_int64]
     L.ieache_ctx_timer_start.argtypes = [c_void_p]
     L.ieache_ctx_timer_stop.argtypes = [c_void_p, POINTER(c_double)]
     L.ieache_measure_fp64_peak.argtypes = [c_void_p, POINTER(c_double)]
@@ -146,6 +148,11 @@ def verif_run(directory: str):
 def set_wide_max(max_gates: int) -> int:
     """Launches of <= max_gates gates use the latency kernel; returns the previous threshold."""
     return lib().ieache_set_wide_max(max_gates)
+
+
+def set_ks_staged_min(min_gates: int) -> int:
+    """Key-switch launches of >= min_gates gates use the staged kernel; returns the previous threshold."""
+    return lib().ieache_set_ks_staged_min(min_gates)
 
 
 def set_cluster_max(max_gates: int) -> int:

@@ -171,6 +171,12 @@ extern "C" int64_t ieache_set_cluster_max(int64_t max_gates)
     if (max_gates >= 0) set_cluster_max(max_gates);
     return old;
 }
+extern "C" int64_t ieache_set_ks_staged_min(int64_t min_gates)
+{
+    const long long old = get_ks_staged_min();
+    if (min_gates >= 0) set_ks_staged_min(min_gates);
+    return old;
+}
 extern "C" int ieache_ctx_timer_start(ieache_ctx *ctx)
 {
     if (!ctx) return fail(IEACHE_ERR_ARG, "null ctx");

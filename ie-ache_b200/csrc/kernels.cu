@@ -971,6 +971,143 @@ keyswitch_cluster_kernel(DevParams p, const int32_t *__restrict__ ksk, GateAddr 
     cluster.sync(); /* keep every CTA's shared memory alive until CTA 0 has read it */
 }
 
+/* throughput variant: the (base-1)*t key rows of one input position i are contiguous in the packed key
+ * (24 rows = 60 672 B at t = 8, base = 4), so ONE bulk copy per position stages them in shared memory for the
+ * kKsGates gates of a CTA; every gate then picks the <= t rows its digits select with 16-byte shared loads.  The
+ * gather kernel above pulls each row from L2 once per gate (15.5 MB per gate, 17 TB/s: the SMs' L2 ports are the
+ * limit); here a CTA pulls the whole key once per kKsGates gates (5.2 MB per gate at 12) and the shared-memory
+ * pipe (128 B/clk) is the limit instead.  Integer adds commute: results are bit-identical.
+ * Roles: kKsGates groups of 64 consumer threads (3 int4 lanes of the 158-lane row each) + one producer warp that
+ * keeps a two-deep ring of row blocks full (mbarrier full/empty pairs). */
+constexpr int kKsGates = 12;
+constexpr int kKsStageThreads = kKsGates * 64 + 32;
+constexpr int kKsRowBytes = kLweStride * 4;
+constexpr int kKsMaxBlockRows = 24;
+constexpr int kKsStageBlockBytes = kKsMaxBlockRows * kKsRowBytes;
+constexpr int kKsStageUWords = 1028;
+constexpr int kKsRing = 3;           /* row blocks in flight: 3 x 60 672 B + 12 samples = 226 KB of the 227 KB a CTA may use */
+constexpr int kKsStageSmem = kKsRing * kKsStageBlockBytes + kKsGates * kKsStageUWords * 4 + 64;
+
+__device__ __forceinline__ void mbar_wait(uint32_t mb, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(mb), "r"(parity) : "memory");
+}
+
+__global__ void __launch_bounds__(kKsStageThreads, 1)
+keyswitch_staged_kernel(DevParams p, const int32_t *__restrict__ ksk, GateAddr ga, int32_t *__restrict__ out_base,
+                        const int32_t *__restrict__ ext, int pair_offset, int32_t cst_post)
+{
+    extern __shared__ __align__(128) unsigned char ks_smem[];
+    int4 *stage = reinterpret_cast<int4 *>(ks_smem);                                   /* [kKsRing][block rows][158] */
+    int32_t *u_all = reinterpret_cast<int32_t *>(ks_smem + kKsRing * kKsStageBlockBytes);    /* [kKsGates][1028] */
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(ks_smem + kKsStageSmem - 64);        /* full[kKsRing], empty[kKsRing] */
+    const int t = p.ks_t, basebit = p.ks_basebit, basem1 = (1 << basebit) - 1;
+    const int block_rows = t * basem1;
+    const uint32_t block_bytes = (uint32_t)block_rows * kKsRowBytes;
+    const int grp = threadIdx.x >> 6, tid = threadIdx.x & 63;
+    const bool producer = grp == kKsGates;
+    const long long total = (long long)ga.ntempl * ga.n_inst;
+    const long long g = (long long)blockIdx.x * kKsGates + grp;
+    const bool active = !producer && g < total;
+
+    if (threadIdx.x == 0) {
+        for (int r = 0; r < kKsRing; r++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar + r)));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar + kKsRing + r)), "r"(kKsGates * 64));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    /* the extracted sample(s) of this group's gate; idle groups use zeros (no digit selects a row) */
+    if (!producer) {
+        int32_t *u = u_all + grp * kKsStageUWords;
+        const int32_t *u0 = active ? ext + (size_t)g * kExtStride : nullptr;
+        const int32_t *u1 = (active && pair_offset > 0) ? ext + ((size_t)g + pair_offset) * kExtStride : nullptr;
+        for (int i = tid; i <= kN; i += 64) u[i] = active ? (u0[i] + (u1 ? u1[i] : 0)) : 0;
+    }
+    __syncthreads();
+
+    if (producer) {
+        if (threadIdx.x == kKsGates * 64) {
+            for (int i = 0; i < kN; i++) {
+                const int b = i % kKsRing, use = i / kKsRing;
+                if (use >= 1) mbar_wait(smem_u32(mbar + kKsRing + b), (uint32_t)(use - 1) & 1u); /* every consumer released the slot */
+                const uint32_t full = smem_u32(mbar + b);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(block_bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_u32(stage) + (uint32_t)b * kKsStageBlockBytes),
+                               "l"(reinterpret_cast<const unsigned char *>(ksk) + (size_t)i * block_bytes), "r"(block_bytes), "r"(full) : "memory");
+            }
+        }
+        return;
+    }
+
+    const int32_t *u = u_all + grp * kKsStageUWords;
+    const uint32_t prec_offset = 1u << (32 - (1 + basebit * t));
+    int4 a0 = make_int4(0, 0, 0, 0), a1 = a0, a2 = a0;
+    const bool third = tid + 128 < kLweStride / 4;
+    for (int i = 0; i < kN; i++) {
+        const int b = i % kKsRing;
+        const uint32_t av = (uint32_t)u[i] + prec_offset;
+        mbar_wait(smem_u32(mbar + b), (uint32_t)(i / kKsRing) & 1u);
+        const int4 *blk = stage + (size_t)b * (kKsStageBlockBytes / 16) + tid;
+        /* digits two at a time: when both select a row the two subtractions fold into one three-input add per word
+         * (the INT32 pipe issues at half rate on this part and was the limit with one add per word and row) */
+#pragma unroll 2
+        for (int j = 0; j + 1 < t; j += 2) {
+            const int d0 = (av >> (32 - (j + 1) * basebit)) & basem1, d1 = (av >> (32 - (j + 2) * basebit)) & basem1;
+            const int4 *r0 = blk + (size_t)(j * basem1 + d0 - 1) * (kLweStride / 4);
+            const int4 *r1 = blk + (size_t)((j + 1) * basem1 + d1 - 1) * (kLweStride / 4);
+            if (d0 && d1) { /* uniform in the group */
+                const int4 p0 = r0[0], q0 = r1[0], p1 = r0[64], q1 = r1[64];
+                a0.x = a0.x - p0.x - q0.x; a0.y = a0.y - p0.y - q0.y; a0.z = a0.z - p0.z - q0.z; a0.w = a0.w - p0.w - q0.w;
+                a1.x = a1.x - p1.x - q1.x; a1.y = a1.y - p1.y - q1.y; a1.z = a1.z - p1.z - q1.z; a1.w = a1.w - p1.w - q1.w;
+                if (third) { const int4 p2 = r0[128], q2 = r1[128]; a2.x = a2.x - p2.x - q2.x; a2.y = a2.y - p2.y - q2.y; a2.z = a2.z - p2.z - q2.z; a2.w = a2.w - p2.w - q2.w; }
+            } else if (d0 | d1) {
+                const int4 *row = d0 ? r0 : r1;
+                const int4 v0 = row[0], v1 = row[64];
+                a0.x -= v0.x; a0.y -= v0.y; a0.z -= v0.z; a0.w -= v0.w;
+                a1.x -= v1.x; a1.y -= v1.y; a1.z -= v1.z; a1.w -= v1.w;
+                if (third) { const int4 v2 = row[128]; a2.x -= v2.x; a2.y -= v2.y; a2.z -= v2.z; a2.w -= v2.w; }
+            }
+        }
+        if (t & 1) {
+            const int j = t - 1, d = (av >> (32 - (j + 1) * basebit)) & basem1;
+            if (d) {
+                const int4 *row = blk + (size_t)(j * basem1 + d - 1) * (kLweStride / 4);
+                const int4 v0 = row[0], v1 = row[64];
+                a0.x -= v0.x; a0.y -= v0.y; a0.z -= v0.z; a0.w -= v0.w;
+                a1.x -= v1.x; a1.y -= v1.y; a1.z -= v1.z; a1.w -= v1.w;
+                if (third) { const int4 v2 = row[128]; a2.x -= v2.x; a2.y -= v2.y; a2.z -= v2.z; a2.w -= v2.w; }
+            }
+        }
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(mbar + kKsRing + b)) : "memory");
+    }
+    if (!active) return;
+    const int e = (int)(g / ga.ntempl), tt = (int)(g - (long long)e * ga.ntempl);
+    const int out_idx = ga.tmpl ? ga.tmpl[tt].out : tt;
+    int32_t *outp = out_base + ((size_t)e * ga.inst_samples + out_idx) * ga.stride;
+    const int32_t bval = u[kN] + cst_post;
+    auto put = [&](int lane, int4 v) {
+        const int w0 = lane * 4;
+        if (p.n >= w0 && p.n < w0 + 4) {
+            if (p.n == w0) v.x += bval; else if (p.n == w0 + 1) v.y += bval;
+            else if (p.n == w0 + 2) v.z += bval; else v.w += bval;
+        }
+        reinterpret_cast<int4 *>(outp)[lane] = v;
+    };
+    put(tid, a0);
+    put(tid + 64, a1);
+    if (third) put(tid + 128, a2);
+}
+
+/* launches of at least this many gates use the staged kernel: one full wave of kKsGates-gate CTAs */
+static long long g_ks_staged_min = [] { const char *e = getenv("IEACHE_KS_STAGED_MIN"); return e ? atoll(e) : 148LL * kKsGates; }();
+void set_ks_staged_min(long long v) { g_ks_staged_min = v; }
+long long get_ks_staged_min() { return g_ks_staged_min; }
+
 cudaError_t launch_keyswitch(const DevParams &p, const int32_t *ksk, const GateAddr &ga, int32_t *out_base,
                              const int32_t *ext, int pair_offset, int32_t cst_post, cudaStream_t s)
 {
@@ -986,6 +1123,19 @@ cudaError_t launch_keyswitch(const DevParams &p, const int32_t *ksk, const GateA
     if (smem > 64 * 1024) return cudaErrorInvalidValue;
     if (count <= g_wide_max && p.ks_t <= 16) {
         keyswitch_cluster_kernel<<<(unsigned)count * kKsCluster, kKsThreads, 0, s>>>(p, ksk, ga, out_base, ext, pair_offset, cst_post);
+        return cudaGetLastError();
+    }
+    /* wide launches: row blocks staged once per kKsGates gates */
+    const int block_rows = p.ks_t * ((1 << p.ks_basebit) - 1);
+    if (block_rows <= kKsMaxBlockRows && count >= g_ks_staged_min) {
+        static bool attr2 = false;
+        if (!attr2) {
+            cudaError_t e = cudaFuncSetAttribute(keyswitch_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKsStageSmem);
+            if (e != cudaSuccess) return e;
+            attr2 = true;
+        }
+        const unsigned grid = (unsigned)((count + kKsGates - 1) / kKsGates);
+        keyswitch_staged_kernel<<<grid, kKsStageThreads, kKsStageSmem, s>>>(p, ksk, ga, out_base, ext, pair_offset, cst_post);
         return cudaGetLastError();
     }
     keyswitch_kernel<<<(unsigned)count, kKsThreads, smem, s>>>(p, ksk, ga, out_base, ext, pair_offset, cst_post);

@@ -82,6 +82,9 @@ long long get_wide_max();
 /* launches with <= cluster_max gates (and <= wide_max) use the 2-CTA-cluster latency kernel (one gate on two SMs) */
 void set_cluster_max(long long v);
 long long get_cluster_max();
+/* key-switch launches with >= ks_staged_min gates use the staged kernel (row blocks shared by 12 gates per CTA) */
+void set_ks_staged_min(long long v);
+long long get_ks_staged_min();
 
 int blind_rotate_smem_bytes(int groups);
 int blind_rotate_groups_per_cta();

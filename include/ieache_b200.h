@@ -74,6 +74,10 @@ int64_t ieache_set_wide_max(int64_t max_gates);
  * pair of SMs (thread-block cluster of 2, products exchanged through distributed shared memory).  Same calling
  * convention as ieache_set_wide_max.  Default 74 (148 SMs / 2: one wave). */
 int64_t ieache_set_cluster_max(int64_t max_gates);
+/* Key-switch launches of at least min_gates gates use the staged kernel (the key rows of one input position are
+ * copied to shared memory once per 12 gates); smaller ones gather rows per gate.  Same calling convention.
+ * Default 1776 (one wave of 12-gate CTAs on 148 SMs).  Both kernels give bit-identical results. */
+int64_t ieache_set_ks_staged_min(int64_t min_gates);
 /* step timer: CUDA events on the engine's stream (torch events only see torch's stream) */
 int ieache_ctx_timer_start(ieache_ctx *ctx);
 int ieache_ctx_timer_stop(ieache_ctx *ctx, double *elapsed_ms); /* records, synchronises, returns the elapsed device time */

@@ -113,6 +113,24 @@ def test_stage_parity(eng, full, kernel_mode):
     assert (eng.keyswitch(key, ext_cpu) == ks.keyswitch(ext_cpu)).all()  # integer path: bit-exact
 
 
+def test_keyswitch_kernels_bit_exact(pkg, eng, full):
+    """the three key-switch kernels (8-CTA cluster, per-gate gather, staged row blocks) are integer sums of the
+    same rows: identical to the oracle and to each other, also for a count that leaves idle groups in a CTA"""
+    ks, key = full
+    rng = np.random.default_rng(5)
+    ext = rng.integers(-2 ** 31, 2 ** 31, size=(29, 1025), dtype=np.int64).astype(np.int32)
+    want = ks.keyswitch(ext)
+    old_w, old_s = pkg.set_wide_max(1 << 40), pkg.set_ks_staged_min(1 << 40)
+    try:
+        assert (eng.keyswitch(key, ext) == want).all()           # cluster kernel (narrow launch)
+        pkg.set_wide_max(0)
+        assert (eng.keyswitch(key, ext) == want).all()           # per-gate gather
+        pkg.set_ks_staged_min(1)
+        assert (eng.keyswitch(key, ext) == want).all()           # staged: 3 CTAs, the last one with 7 idle groups
+    finally:
+        pkg.set_wide_max(old_w); pkg.set_ks_staged_min(old_s)
+
+
 def test_aliasing_and_empty(eng, full, kernel_mode):
     ks, key = full
     a, b = ks.encrypt([1, 1, 0], 1), ks.encrypt([1, 0, 0], 2)
