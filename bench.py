@@ -136,6 +136,75 @@ def run_reference(args):
     return 0
 
 
+def run_circuit_workload(args, m, eng, sk, key, rank, world, local, t_bcast_ms):
+    """BASELINE.json configs 4 / 5, time-boxed: --n-expr independent expressions per GPU and step through the levelised
+    circuit (every level = one blind-rotation + one key-switch launch over all expressions); sharded by expression,
+    cloud key replicated, no data-path collective.  A step = one evaluation of all expressions of this rank."""
+    import torch
+    import torch.distributed as dist
+    kind, width, name = (m.CIRC_MULADD, 32, "a*b+c (mul32 then 64-bit add)") if args.workload == "muladd" else (m.CIRC_MUL, 64, "64-bit multiply (2 x mul64 + split)")
+    circ = eng.circuit(kind, width)
+    n_expr = args.n_expr
+    rng = np.random.default_rng(4000 + rank)
+    nw = circ.n_inputs // 32
+    vals = rng.integers(0, 2 ** 31, size=(n_expr, nw), dtype=np.int64)
+    vals[:, -1] = 0                                   # carry block: encryptions of 0
+    if kind == m.CIRC_MULADD:
+        vals[:, 3] = 0                                # high chunk of c
+    bits = ((vals[:, :, None] >> np.arange(32)) & 1).astype(np.int32).reshape(-1)
+    d_in = eng.device_alloc(bits.size * m.DEVICE_STRIDE * 4)
+    d_res = eng.device_alloc(n_expr * circ.n_outputs * m.DEVICE_STRIDE * 4)
+    sk.encrypt_to_device(bits, d_in, seed=500 + rank)
+
+    def barrier():
+        eng.sync()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        eng.eval_device(key, circ, d_in, d_res, n_expr)
+    sampler = ClockSampler(local)
+    barrier()
+    launches0 = eng.launch_count
+    sampler.start()
+    eng.timer_start()
+    for _ in range(args.steps):
+        eng.eval_device(key, circ, d_in, d_res, n_expr)
+    ms_total = eng.timer_stop()
+    clocks = sampler.stop()
+    barrier()
+    launches = eng.launch_count - launches0
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    out_bits = sk.decrypt_from_device(d_res, n_expr * circ.n_outputs).reshape(n_expr, -1, 32).astype(np.int64)
+    words = (out_bits << np.arange(32)).sum(axis=2)
+    for e in range(n_expr):
+        got = sum(int(w) << (32 * i) for i, w in enumerate(words[e]))
+        v = [int(x) for x in vals[e]]
+        want = v[0] * v[1] + v[2] if kind == m.CIRC_MULADD else (v[0] | v[1] << 32) * (v[2] | v[3] << 32)
+        if got != want:
+            raise SystemExit(f"rank {rank}: expression {e} decrypts to {got}, expected {want}")
+    value = world * n_expr * circ.bootstraps * args.steps / (ms_total * 1e-3)
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32 torus + f64 transform", "data": "synthetic",
+            "config": {"workload": f"{n_expr} independent {name} per GPU and step: {circ.bootstraps} bootstraps, {circ.levels} levels each "
+                                   f"(time-boxed subset of BASELINE.json config {'4' if kind == m.CIRC_MULADD else '5'})",
+                       "params": "n=630,N=1024,k=1,l=3,Bgbit=7,t=8,basebit=2", "parallelism": f"dp{world} by expression (key replicated, no data-path collective)",
+                       "ms_per_expression": ms_total / args.steps / n_expr, "key_broadcast_ms": t_bcast_ms,
+                       "verified": "every decrypted result equals the plaintext arithmetic"},
+            "e2e": None, "gpu_launches": launches, "clocks": clocks, "roofline": None, "cpu_baseline": None}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -144,6 +213,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log2-gates", type=int, default=20, help="gates per step and per GPU (default 2^20, BASELINE.json config 2)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--workload", default="nand", choices=["nand", "muladd", "mul64"],
+                    help="nand: BASELINE.json config 2 (the metric's configuration, default); muladd / mul64: a time-boxed subset of "
+                         "configs 4 / 5 (independent a*b+c expressions / 64-bit multiplies, --n-expr per GPU) through the levelised circuits")
+    ap.add_argument("--n-expr", type=int, default=64, help="expressions per GPU and step for --workload muladd / mul64")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-expression", action="store_true")
     args = ap.parse_args()
@@ -191,6 +264,9 @@ def main():
             both = kt.cpu().numpy()
             lwe, tlwe = both[:N_LWE].copy(), both[N_LWE:].copy()
             sk = eng.secret_key_import(params, lwe, tlwe)
+
+    if args.workload != "nand":
+        return run_circuit_workload(args, m, eng, sk, key, rank, world, local, t_bcast_ms)
 
     # ---- synthetic ciphertexts, made on the GPU (Client/alice.c's role): 2 x count samples, resident in HBM
     rng = np.random.default_rng(1000 + rank)

@@ -124,11 +124,11 @@ constexpr int kGroupSmem = kAccBytes + 2 * kBufBytes + kAbarBytes; /* 28704 */
 /* L = gadget length, G = gates (64-thread groups) per CTA, MINB = CTAs per SM the register
  * allocation is tuned for, ROLL = 0 unrolled step body, 1 rolled over both loops, 2 rolled over digits only, 3 over polynomials only: the
  * step body fits the 32 KB instruction cache (the fully unrolled body is ~60 KB of SASS) */
-template <int L, int G, int MINB, int ROLL, bool NOBK = false, bool LOCK = false, bool SPREAD = false>
+template <int L, int G, int MINB, int ROLL, int NOBK = 0, bool LOCK = false, bool SPREAD = false>
 __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
                     const int32_t *__restrict__ baseB, int32_t *__restrict__ ext);
 
-template <int L, int G, int MINB, int ROLL, bool NOBK = false, bool LOCK = false, bool SPREAD = false>
+template <int L, int G, int MINB, int ROLL, int NOBK = 0, bool LOCK = false, bool SPREAD = false>
 __global__ void __launch_bounds__(64 * G, MINB)
 blind_rotate_kernel(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
                     const int32_t *__restrict__ baseB, int32_t *__restrict__ ext)
@@ -144,7 +144,7 @@ blind_rotate_kernel_r200(DevParams p, const double2 *__restrict__ bkfft, GateAdd
     blind_rotate_body<L, 1, 5, 0, false, false>(p, bkfft, ga, baseA, baseB, ext);
 }
 
-template <int L, int G, int MINB, int ROLL, bool NOBK, bool LOCK, bool SPREAD>
+template <int L, int G, int MINB, int ROLL, int NOBK, bool LOCK, bool SPREAD>
 __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
                     const int32_t *__restrict__ baseB, int32_t *__restrict__ ext)
 {
@@ -246,8 +246,11 @@ __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__
                 fwd_transform(xr, xi, buf, tid, bar, w1, w2, w3);
 #pragma unroll
                 for (int r = 0; r < 8; r++) {
-                    const double2 b0 = NOBK ? make_double2(1.0 + r, 0.5) : __ldg(bk_r + r * 64);
-                    const double2 b1 = NOBK ? make_double2(0.25, 2.0 - r) : __ldg(bk_r + kHalfN + r * 64);
+                    /* NOBK (timing experiments, wrong results): 1 = no loads at all, 2 = the same 16-byte loads from a
+                     * 16 KB shared-memory row (what a TMA-staged BK_i would cost the LSU, without its L2 latency) */
+                    const double2 *fake = reinterpret_cast<const double2 *>(smem_raw + (size_t)G * kGroupSmem) + tid;
+                    const double2 b0 = NOBK == 1 ? make_double2(1.0 + r, 0.5) : (NOBK == 2 ? fake[r * 64] : __ldg(bk_r + r * 64));
+                    const double2 b1 = NOBK == 1 ? make_double2(0.25, 2.0 - r) : (NOBK == 2 ? fake[kHalfN + r * 64] : __ldg(bk_r + kHalfN + r * 64));
                     cmac(s0r[r], s0i[r], xr[r], xi[r], b0.x, b0.y);
                     cmac(s1r[r], s1i[r], xr[r], xi[r], b1.x, b1.y);
                 }
@@ -397,8 +400,8 @@ blind_rotate_wide_kernel(DevParams p, const double2 *__restrict__ bkfft, GateAdd
  * moves 192 KB and is LSU-bound at 72 %: profiles/README.md). */
 constexpr int pair_smem_bytes() { return kAccBytes + 2 * 2 * kBufBytes + 2 * kHalfN * 16 + kAbarBytes; }
 
-template <int L>
-__global__ void __launch_bounds__(128, 2)
+template <int L, int MINB = 2>
+__global__ void __launch_bounds__(128, MINB)
 blind_rotate_pair_kernel(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
                          const int32_t *__restrict__ baseB, int32_t *__restrict__ ext)
 {
@@ -470,9 +473,15 @@ blind_rotate_pair_kernel(DevParams p, const double2 *__restrict__ bkfft, GateAdd
             /* the row's 16 KB of BK_i are requested before the transform: with one gate per SM nothing else hides
              * the L2 latency (the barriers inside the transform keep the compiler from sinking the loads) */
             double2 b0[8], b1[8];
+            if (MINB <= 2) {
 #pragma unroll
-            for (int r = 0; r < 8; r++) { b0[r] = __ldg(bk_mine + pp * kRowElems + r * 64); b1[r] = __ldg(bk_other + pp * kRowElems + r * 64); }
+                for (int r = 0; r < 8; r++) { b0[r] = __ldg(bk_mine + pp * kRowElems + r * 64); b1[r] = __ldg(bk_other + pp * kRowElems + r * 64); }
+            }
             fwd_transform(xr, xi, buf, tid, grp, w1, w2, w3);
+            if (MINB > 2) { /* three CTAs per SM leave 168 registers: no room to hold a row across the transform */
+#pragma unroll
+                for (int r = 0; r < 8; r++) { b0[r] = __ldg(bk_mine + pp * kRowElems + r * 64); b1[r] = __ldg(bk_other + pp * kRowElems + r * 64); }
+            }
 #pragma unroll
             for (int r = 0; r < 8; r++) {
                 cmac(mr[r], mi[r], xr[r], xi[r], b0[r].x, b0[r].y);
@@ -729,6 +738,13 @@ static cudaError_t launch_br_pair(const DevParams &p, const double2 *bkfft, cons
                                   const int32_t *baseB, int32_t *ext, long long count, cudaStream_t s)
 {
     constexpr int smem = pair_smem_bytes();
+    static const bool three = getenv("IEACHE_PAIR_3CTA") != nullptr; /* experiment: 3 CTAs per SM at 168 registers */
+    if (three) {
+        cudaError_t e = cudaFuncSetAttribute(blind_rotate_pair_kernel<L, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        blind_rotate_pair_kernel<L, 3><<<(int)count, 128, smem, s>>>(p, bkfft, ga, baseA, baseB, ext);
+        return cudaGetLastError();
+    }
     cudaError_t e = cudaFuncSetAttribute(blind_rotate_pair_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     blind_rotate_pair_kernel<L><<<(int)count, 128, smem, s>>>(p, bkfft, ga, baseA, baseB, ext);
@@ -766,11 +782,11 @@ static int br_variant()
 int blind_rotate_groups_per_cta() { const int v = br_variant(); return (v == 4 || v == 11 || v == 13 || v == 31 || v == 34) ? 4 : ((v == 0 || v == 1 || v == 3 || v == 5 || v == 6 || v == 12 || v == 30 || v == 32 || v == 33) ? 2 : 1); }
 int blind_rotate_smem_bytes(int groups) { return groups * kGroupSmem; }
 
-template <int L, int G, int MINB, int ROLL, bool NOBK = false, bool LOCK = false, bool SPREAD = false>
+template <int L, int G, int MINB, int ROLL, int NOBK = 0, bool LOCK = false, bool SPREAD = false>
 static cudaError_t launch_br_variant(const DevParams &p, const double2 *bkfft, const GateAddr &ga, const int32_t *baseA,
                                      const int32_t *baseB, int32_t *ext, long long count, cudaStream_t s)
 {
-    const int smem = G * kGroupSmem;
+    const int smem = G * kGroupSmem + (NOBK == 2 ? 2 * kHalfN * 16 : 0);
     const int grid = (int)((count + G - 1) / G);
     cudaError_t e = cudaFuncSetAttribute(blind_rotate_kernel<L, G, MINB, ROLL, NOBK, LOCK, SPREAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
@@ -789,7 +805,17 @@ cudaError_t launch_blind_rotate(const DevParams &p, const double2 *bkfft, const 
         if (p.l == 3) return launch_br_cluster<3>(p, bkfft, ga, baseA, baseB, ext, count, s);
         if (p.l == 2) return launch_br_cluster<2>(p, bkfft, ga, baseA, baseB, ext, count, s);
     }
-    if (count <= g_wide_max) {
+    /* The throughput kernel holds 4 gates per SM, so its time moves in steps of 4 x SMs gates (592: 5.8 ms, 720:
+     * 9.3 ms); the two-group kernel holds 2 gates per SM at 97 % of the throughput kernel's full-wave rate and
+     * finer steps (720 gates: 7.4 ms).  Launches that would leave more than 10 % of the throughput kernel's last
+     * wave empty therefore also use it (measured table in DESIGN.md 4.2). */
+    bool two_group = count <= g_wide_max;
+    if (!two_group && g_wide_max > 0) {
+        static const long long slots = [] { int d = 0, sms = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d); return 4LL * sms; }();
+        const long long waves = (count + slots - 1) / slots;
+        two_group = count * 10 < waves * slots * 9;
+    }
+    if (two_group) {
         static const int lat = [] { const char *e = getenv("IEACHE_LATENCY_KERNEL"); return e ? atoi(e) : 2; }();
         if (lat == 6) {
             if (p.l == 3) return launch_br_wide<3>(p, bkfft, ga, baseA, baseB, ext, count, s);
@@ -831,6 +857,8 @@ cudaError_t launch_blind_rotate(const DevParams &p, const double2 *bkfft, const 
     case 13: return launch_br_variant<3, 4, 1, 0, false, false>(p, bkfft, ga, baseA, baseB, ext, count, s);
     /* timing experiments only (wrong results): no BK loads */
     case 107: return launch_br_variant<3, 1, 4, 0, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 207: return launch_br_variant<3, 1, 4, 2, 2>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 208: return launch_br_variant<3, 1, 5, 2, 2>(p, bkfft, ga, baseA, baseB, ext, count, s);
     case 109: return launch_br_variant<3, 1, 6, 0, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
     case 102: return launch_br_variant<3, 1, 6, 1, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
     case 1: return launch_br_variant<3, 2, 3, 1>(p, bkfft, ga, baseA, baseB, ext, count, s);
@@ -1103,8 +1131,9 @@ keyswitch_staged_kernel(DevParams p, const int32_t *__restrict__ ksk, GateAddr g
     if (third) put(tid + 128, a2);
 }
 
-/* launches of at least this many gates use the staged kernel: one full wave of kKsGates-gate CTAs */
-static long long g_ks_staged_min = [] { const char *e = getenv("IEACHE_KS_STAGED_MIN"); return e ? atoll(e) : 148LL * kKsGates; }();
+/* launches of at least this many gates use the staged kernel: a CTA needs ~0.96 ms for its 12 gates whatever the
+ * launch size, the gather kernel ~0.95 us per gate, so they cross near 1000 gates */
+static long long g_ks_staged_min = [] { const char *e = getenv("IEACHE_KS_STAGED_MIN"); return e ? atoll(e) : 1000LL; }();
 void set_ks_staged_min(long long v) { g_ks_staged_min = v; }
 long long get_ks_staged_min() { return g_ks_staged_min; }
 

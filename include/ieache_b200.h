@@ -76,7 +76,7 @@ int64_t ieache_set_wide_max(int64_t max_gates);
 int64_t ieache_set_cluster_max(int64_t max_gates);
 /* Key-switch launches of at least min_gates gates use the staged kernel (the key rows of one input position are
  * copied to shared memory once per 12 gates); smaller ones gather rows per gate.  Same calling convention.
- * Default 1776 (one wave of 12-gate CTAs on 148 SMs).  Both kernels give bit-identical results. */
+ * Default 1000 (where the two kernels cross).  Both kernels give bit-identical results. */
 int64_t ieache_set_ks_staged_min(int64_t min_gates);
 /* step timer: CUDA events on the engine's stream (torch events only see torch's stream) */
 int ieache_ctx_timer_start(ieache_ctx *ctx);
