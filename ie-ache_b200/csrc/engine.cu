@@ -54,6 +54,9 @@ struct ieache_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t ks_stream = nullptr;   /* key switches of chunk c overlap the blind rotation of chunk c+1 */
     cudaEvent_t ev_br[2] = {nullptr, nullptr}, ev_ks[2] = {nullptr, nullptr};
+    /* host-buffer calls: chunk k+1 is copied in and chunk k-1 copied out while chunk k computes */
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     /* measured on B200 (profiles/README.md): running the key switch under the next blind rotation is
      * SLOWER (92k vs 98k gates/s) — its gather stream evicts the bootstrapping key from L2 and its CTAs
      * displace blind-rotation CTAs — so the overlap is off unless IEACHE_OVERLAP_KS=1 */
@@ -72,7 +75,12 @@ struct ieache_ctx {
 static int ensure(ieache_ctx *ctx, int32_t **buf, size_t *cap, size_t words)
 {
     if (*cap >= words) return IEACHE_OK;
-    if (*buf) { cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->ks_stream); cudaFree(*buf); *buf = nullptr; *cap = 0; }
+    if (*buf) {
+        cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->ks_stream);
+        if (ctx->h2d_stream) cudaStreamSynchronize(ctx->h2d_stream);
+        if (ctx->d2h_stream) cudaStreamSynchronize(ctx->d2h_stream);
+        cudaFree(*buf); *buf = nullptr; *cap = 0;
+    }
     CU(cudaMalloc((void **)buf, words * sizeof(int32_t)));
     *cap = words;
     return IEACHE_OK;
@@ -94,9 +102,14 @@ extern "C" int ieache_ctx_create(int device, ieache_ctx **out)
     int prio_lo = 0, prio_hi = 0;
     CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     CU(cudaStreamCreateWithPriority(&ctx->ks_stream, cudaStreamNonBlocking, prio_hi));
+    CU(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) {
         CU(cudaEventCreateWithFlags(&ctx->ev_br[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ctx->ev_ks[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
     }
     CU(upload_twiddles());
     const char *ov = getenv("IEACHE_OVERLAP_KS");
@@ -114,7 +127,12 @@ extern "C" void ieache_ctx_destroy(ieache_ctx *ctx)
     for (int i = 0; i < 4; i++) cudaFree(ctx->d_stage[i]);
     cudaFree(ctx->d_wires);
     cudaStreamSynchronize(ctx->ks_stream);
-    for (int i = 0; i < 2; i++) { cudaEventDestroy(ctx->ev_br[i]); cudaEventDestroy(ctx->ev_ks[i]); }
+    cudaStreamSynchronize(ctx->h2d_stream); cudaStreamSynchronize(ctx->d2h_stream);
+    for (int i = 0; i < 2; i++) {
+        cudaEventDestroy(ctx->ev_br[i]); cudaEventDestroy(ctx->ev_ks[i]);
+        cudaEventDestroy(ctx->ev_in[i]); cudaEventDestroy(ctx->ev_done[i]); cudaEventDestroy(ctx->ev_out[i]);
+    }
+    cudaStreamDestroy(ctx->h2d_stream); cudaStreamDestroy(ctx->d2h_stream);
     cudaStreamDestroy(ctx->ks_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -594,17 +612,44 @@ extern "C" int ieache_gate_batch(ieache_ctx *ctx, const ieache_cloudkey *key, in
     if (count == 0) return IEACHE_OK;
     CU(cudaSetDevice(ctx->device));
     const int n = key->p.n;
+    const size_t row = (size_t)(n + 1) * 4;
     const int32_t *src[3] = {a, b, c};
+    /* chunks of <= 65536 gates through two staging slots: the inputs of chunk k+1 go up on their own stream and the
+     * results of chunk k-1 come down on a third one while chunk k computes (pinned host buffers make the copies
+     * asynchronous; pageable ones still work, serialised by the driver) */
+    const size_t per = std::min(count, kChunk);
     int rc;
     for (int i = 0; i < 4; i++)
         if (i == 3 || src[i])
-            if ((rc = ensure(ctx, &ctx->d_stage[i], &ctx->stage_cap[i], count * kLweStride))) return rc;
-    for (int i = 0; i < 3; i++)
-        if (src[i] && (rc = ieache_samples_to_device(ctx, ctx->d_stage[i], src[i], count, n))) return rc;
-    rc = ieache_gate_batch_device(ctx, key, op, ctx->d_stage[3], a ? ctx->d_stage[0] : nullptr, b ? ctx->d_stage[1] : nullptr,
-                                  c ? ctx->d_stage[2] : nullptr, imm, count);
-    if (rc) return rc;
-    return ieache_samples_to_host(ctx, out, ctx->d_stage[3], count, n);
+            if ((rc = ensure(ctx, &ctx->d_stage[i], &ctx->stage_cap[i], 2 * per * kLweStride))) return rc;
+    /* everything queued earlier on the context stream (and its use of the staging buffers) comes first */
+    CU(cudaEventRecord(ctx->ev_done[0], ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->h2d_stream, ctx->ev_done[0], 0));
+    size_t chunk = 0;
+    for (size_t off = 0; off < count; off += per, chunk++) {
+        const size_t m = std::min(per, count - off);
+        const int slot = (int)(chunk & 1);
+        const size_t so = (size_t)slot * per * kLweStride;
+        if (chunk >= 2) CU(cudaStreamWaitEvent(ctx->h2d_stream, ctx->ev_done[slot], 0)); /* chunk-2 no longer reads these inputs */
+        for (int i = 0; i < 3; i++)
+            if (src[i])
+                CU(cudaMemcpy2DAsync(ctx->d_stage[i] + so, kLweStride * 4, src[i] + off * (size_t)(n + 1), row, row, m,
+                                     cudaMemcpyHostToDevice, ctx->h2d_stream));
+        CU(cudaEventRecord(ctx->ev_in[slot], ctx->h2d_stream));
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[slot], 0));
+        if (chunk >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[slot], 0));      /* chunk-2's results have left the slot */
+        rc = ieache_gate_batch_device(ctx, key, op, ctx->d_stage[3] + so, a ? ctx->d_stage[0] + so : nullptr,
+                                      b ? ctx->d_stage[1] + so : nullptr, c ? ctx->d_stage[2] + so : nullptr, imm, m);
+        if (rc) return rc;
+        CU(cudaEventRecord(ctx->ev_done[slot], ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_done[slot], 0));
+        CU(cudaMemcpy2DAsync(out + off * (size_t)(n + 1), row, ctx->d_stage[3] + so, kLweStride * 4, row, m, cudaMemcpyDeviceToHost,
+                             ctx->d2h_stream));
+        CU(cudaEventRecord(ctx->ev_out[slot], ctx->d2h_stream));
+    }
+    CU(cudaStreamSynchronize(ctx->d2h_stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return IEACHE_OK;
 }
 
 extern "C" int ieache_bootstrap_woks(ieache_ctx *ctx, const ieache_cloudkey *key, int32_t *ext_out, const int32_t *x, size_t count)
