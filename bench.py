@@ -335,7 +335,7 @@ def main():
     # memory view: BK streamed once per launch (reuse across all gates of the launch) + per-gate inputs/outputs
     alg_bytes = BK_BYTES + gates_per_launch * (2 * 2524 + 4100)
     roofline = {
-        "kernel": "blind_rotate_kernel<L=3,G=1,MINB=4,ROLL=2>", "bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+        "kernel": "blind_rotate_kernel<L=3,G=1,MINB=4,ROLL=0,ACCREG>", "bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
         "frac": achieved_tflops / fp64_peak if fp64_peak else None, "traffic": traffic,
         "peak_source": "dense FP64 FMA microbenchmark run live by this bench (MEASURED_PEAKS.json has no FP64 figure)",
         "flop_per_gate": FLOP_PER_BOOTSTRAP, "gates_per_launch": gates_per_launch, "ms_per_launch": br_ms,

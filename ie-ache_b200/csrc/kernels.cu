@@ -124,16 +124,16 @@ constexpr int kGroupSmem = kAccBytes + 2 * kBufBytes + kAbarBytes; /* 28704 */
 /* L = gadget length, G = gates (64-thread groups) per CTA, MINB = CTAs per SM the register
  * allocation is tuned for, ROLL = 0 unrolled step body, 1 rolled over both loops, 2 rolled over digits only, 3 over polynomials only: the
  * step body fits the 32 KB instruction cache (the fully unrolled body is ~60 KB of SASS) */
-template <int L, int G, int MINB, int ROLL, int NOBK = 0, bool LOCK = false, bool SPREAD = false>
+template <int L, int G, int MINB, int ROLL, int NOBK = 0, bool LOCK = false, bool SPREAD = false, bool ACCREG = false>
 __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
                     const int32_t *__restrict__ baseB, int32_t *__restrict__ ext);
 
-template <int L, int G, int MINB, int ROLL, int NOBK = 0, bool LOCK = false, bool SPREAD = false>
+template <int L, int G, int MINB, int ROLL, int NOBK = 0, bool LOCK = false, bool SPREAD = false, bool ACCREG = false>
 __global__ void __launch_bounds__(64 * G, MINB)
 blind_rotate_kernel(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
                     const int32_t *__restrict__ baseB, int32_t *__restrict__ ext)
 {
-    blind_rotate_body<L, G, MINB, ROLL, NOBK, LOCK, SPREAD>(p, bkfft, ga, baseA, baseB, ext);
+    blind_rotate_body<L, G, MINB, ROLL, NOBK, LOCK, SPREAD, ACCREG>(p, bkfft, ga, baseA, baseB, ext);
 }
 /* same body with an explicit register cap (5 CTAs of 64 threads per SM at 200 registers) */
 template <int L>
@@ -144,7 +144,7 @@ blind_rotate_kernel_r200(DevParams p, const double2 *__restrict__ bkfft, GateAdd
     blind_rotate_body<L, 1, 5, 0, false, false>(p, bkfft, ga, baseA, baseB, ext);
 }
 
-template <int L, int G, int MINB, int ROLL, int NOBK, bool LOCK, bool SPREAD>
+template <int L, int G, int MINB, int ROLL, int NOBK, bool LOCK, bool SPREAD, bool ACCREG>
 __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
                     const int32_t *__restrict__ baseB, int32_t *__restrict__ ext)
 {
@@ -213,6 +213,15 @@ __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__
     constexpr int kRowElems = 2 * kHalfN;        /* one BK row: 2 output polys x 512 points */
     constexpr int kBkStride = 2 * L * kRowElems; /* elements per BK_i */
     int toggle = 0;
+    /* ACCREG: the 32 ACC coefficients this thread reads unrotated and later updates stay in registers, so a step
+     * only loads the rotated operand and stores the updated value (-128 of 3 135 LSU wavefronts per gate-step) */
+    int32_t areg[2][16];
+    if (ACCREG) {
+#pragma unroll
+        for (int q = 0; q < 2; q++)
+#pragma unroll
+            for (int h = 0; h < 16; h++) areg[q][h] = acc[q * kN + tid + 64 * (h & 7) + 512 * (h >> 3)];
+    }
 
     /* 3. n CMux steps */
     for (int i = 0; i < n; i++) {
@@ -231,7 +240,17 @@ __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__
 #pragma unroll((ROLL == 1 || ROLL == 3) ? 1 : 2)
         for (int q = 0; q < 2; q++) {
             int32_t c[16];
-            rot_minus_one(acc + q * kN, tid, a, c);
+            if (ACCREG) {
+                const int t0 = tid - a;
+#pragma unroll
+                for (int h = 0; h < 16; h++) {
+                    const int t = t0 + 64 * (h & 7) + 512 * (h >> 3);
+                    const int32_t v = acc[q * kN + (t & (kN - 1))];
+                    c[h] = ((t & kN) ? -v : v) - areg[q][h];
+                }
+            } else {
+                rot_minus_one(acc + q * kN, tid, a, c);
+            }
 #pragma unroll((ROLL == 1 || ROLL == 2) ? 1 : L)
             for (int pp = 0; pp < L; pp++) {
                 const int shift = 32 - (pp + 1) * Bgbit;
@@ -258,16 +277,26 @@ __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__
             }
         }
         /* inverse transforms and ACC update; the second pass reuses the code of the first */
-#pragma unroll((ROLL != 0) ? 1 : 2)
+#pragma unroll((ROLL != 0 && !ACCREG) ? 1 : 2)
         for (int j = 0; j < 2; j++) {
             cd *buf = toggle ? bufB : bufA;
             toggle ^= 1;
             inv_transform(s0r, s0i, buf, tid, bar, w1, w2, w3);
             int32_t *accj = acc + j * kN;
+            if (ACCREG) {
 #pragma unroll
-            for (int m = 0; m < 8; m++) {
-                accj[tid + 64 * m] += round_to_torus(s0r[m]);
-                accj[tid + 64 * m + 512] += round_to_torus(s0i[m]);
+                for (int m = 0; m < 8; m++) {
+                    areg[j][m] += round_to_torus(s0r[m]);
+                    areg[j][8 + m] += round_to_torus(s0i[m]);
+                    accj[tid + 64 * m] = areg[j][m];
+                    accj[tid + 64 * m + 512] = areg[j][8 + m];
+                }
+            } else {
+#pragma unroll
+                for (int m = 0; m < 8; m++) {
+                    accj[tid + 64 * m] += round_to_torus(s0r[m]);
+                    accj[tid + 64 * m + 512] += round_to_torus(s0i[m]);
+                }
             }
 #pragma unroll
             for (int r = 0; r < 8; r++) { s0r[r] = s1r[r]; s0i[r] = s1i[r]; }
@@ -776,21 +805,21 @@ static cudaError_t launch_br_wide(const DevParams &p, const double2 *bkfft, cons
 static int br_variant()
 {
     static int v = -1;
-    if (v < 0) { const char *e = getenv("IEACHE_BR_VARIANT"); v = e ? atoi(e) : 23; }
+    if (v < 0) { const char *e = getenv("IEACHE_BR_VARIANT"); v = e ? atoi(e) : 41; }
     return v;
 }
 int blind_rotate_groups_per_cta() { const int v = br_variant(); return (v == 4 || v == 11 || v == 13 || v == 31 || v == 34) ? 4 : ((v == 0 || v == 1 || v == 3 || v == 5 || v == 6 || v == 12 || v == 30 || v == 32 || v == 33) ? 2 : 1); }
 int blind_rotate_smem_bytes(int groups) { return groups * kGroupSmem; }
 
-template <int L, int G, int MINB, int ROLL, int NOBK = 0, bool LOCK = false, bool SPREAD = false>
+template <int L, int G, int MINB, int ROLL, int NOBK = 0, bool LOCK = false, bool SPREAD = false, bool ACCREG = false>
 static cudaError_t launch_br_variant(const DevParams &p, const double2 *bkfft, const GateAddr &ga, const int32_t *baseA,
                                      const int32_t *baseB, int32_t *ext, long long count, cudaStream_t s)
 {
     const int smem = G * kGroupSmem + (NOBK == 2 ? 2 * kHalfN * 16 : 0);
     const int grid = (int)((count + G - 1) / G);
-    cudaError_t e = cudaFuncSetAttribute(blind_rotate_kernel<L, G, MINB, ROLL, NOBK, LOCK, SPREAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(blind_rotate_kernel<L, G, MINB, ROLL, NOBK, LOCK, SPREAD, ACCREG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    blind_rotate_kernel<L, G, MINB, ROLL, NOBK, LOCK, SPREAD><<<grid, 64 * G, smem, s>>>(p, bkfft, ga, baseA, baseB, ext);
+    blind_rotate_kernel<L, G, MINB, ROLL, NOBK, LOCK, SPREAD, ACCREG><<<grid, 64 * G, smem, s>>>(p, bkfft, ga, baseA, baseB, ext);
     return cudaGetLastError();
 }
 
@@ -857,13 +886,16 @@ cudaError_t launch_blind_rotate(const DevParams &p, const double2 *bkfft, const 
     case 13: return launch_br_variant<3, 4, 1, 0, false, false>(p, bkfft, ga, baseA, baseB, ext, count, s);
     /* timing experiments only (wrong results): no BK loads */
     case 107: return launch_br_variant<3, 1, 4, 0, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 40: return launch_br_variant<3, 1, 4, 2, 0, false, false, true>(p, bkfft, ga, baseA, baseB, ext, count, s); /* ACC in registers */
+    case 41: return launch_br_variant<3, 1, 4, 0, 0, false, false, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
     case 207: return launch_br_variant<3, 1, 4, 2, 2>(p, bkfft, ga, baseA, baseB, ext, count, s);
     case 208: return launch_br_variant<3, 1, 5, 2, 2>(p, bkfft, ga, baseA, baseB, ext, count, s);
     case 109: return launch_br_variant<3, 1, 6, 0, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
     case 102: return launch_br_variant<3, 1, 6, 1, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
     case 1: return launch_br_variant<3, 2, 3, 1>(p, bkfft, ga, baseA, baseB, ext, count, s);
     case 7: return launch_br_variant<3, 1, 4, 0>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    default: return launch_br_variant<3, 1, 4, 2>(p, bkfft, ga, baseA, baseB, ext, count, s); /* 23: as fast as the fully unrolled body (7) at half the code size */
+    case 23: return launch_br_variant<3, 1, 4, 2>(p, bkfft, ga, baseA, baseB, ext, count, s); /* as fast as the fully unrolled body (7) at half the code size */
+    default: return launch_br_variant<3, 1, 4, 0, 0, false, false, true>(p, bkfft, ga, baseA, baseB, ext, count, s); /* 41: ACC coefficients in registers, +1.2 % over 23 */
     }
 }
 
