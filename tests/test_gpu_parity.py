@@ -131,6 +131,18 @@ def test_keyswitch_kernels_bit_exact(pkg, eng, full):
         pkg.set_wide_max(old_w); pkg.set_ks_staged_min(old_s)
 
 
+def test_keyswitch_staged_small_lwe_dimension(pkg, eng, small):
+    """staged key switch when the LWE dimension is far below the 632-word row (n = 8): rows are zero-padded"""
+    ks, _, key = small
+    rng = np.random.default_rng(6)
+    ext = rng.integers(-2 ** 31, 2 ** 31, size=(13, 1025), dtype=np.int64).astype(np.int32)
+    old_w, old_s = pkg.set_wide_max(0), pkg.set_ks_staged_min(1)
+    try:
+        assert (eng.keyswitch(key, ext) == ks.keyswitch(ext)).all()
+    finally:
+        pkg.set_wide_max(old_w); pkg.set_ks_staged_min(old_s)
+
+
 def test_aliasing_and_empty(eng, full, kernel_mode):
     ks, key = full
     a, b = ks.encrypt([1, 1, 0], 1), ks.encrypt([1, 0, 0], 2)
