@@ -112,6 +112,7 @@ def lib() -> ctypes.CDLL:
     L.ieache_session_compute.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, POINTER(c_size_t), POINTER(c_double)]
     L.ieache_session_compute_batch.argtypes = [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_double)]
     L.ieache_session_eval_postfix.argtypes = [c_void_p, c_char_p, c_size_t, c_void_p, c_int, c_void_p, c_void_p, POINTER(c_double)]
+    L.ieache_session_compute_dirs.argtypes = [c_void_p, c_size_t, c_void_p, c_void_p, POINTER(c_double)]
     L.ieache_keygen_files.argtypes = [c_void_p, c_char_p, POINTER(Params), c_uint64, c_uint64]
     L.ieache_alice_encrypt.argtypes = [c_char_p, c_int32, c_int32, c_void_p, c_char_p, c_int]
     L.ieache_alice_run.argtypes = [c_char_p]
@@ -296,6 +297,16 @@ class Session:
                                                _ptr(ans), counts.ctypes.data_as(c_void_p), byref(secs))
         _check(rc)
         return rc, ans, counts, secs.value
+
+    def compute_dirs(self, directories):
+        """batched ingest: every directory holds cloud.data + operator.txt and receives answer.data, as if ./cloud
+        had run there; one levelised batch for all of them -> (exit_codes, seconds)"""
+        n = len(directories)
+        arr = (ctypes.c_char_p * n)(*[d.encode() for d in directories])
+        codes = np.zeros(n, dtype=np.int32)
+        secs = c_double()
+        _check(lib().ieache_session_compute_dirs(self._h, n, arr, _ptr(codes), byref(secs)))
+        return codes, secs.value
 
     def close(self):
         if self._h:

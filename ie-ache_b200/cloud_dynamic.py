@@ -76,5 +76,11 @@ class CloudNode:
         write_block(os.path.join(self.dir, "answer.data"), ans[0][:int(counts[0])], self.variance)
         return rc
 
+    def compute_many(self, directories: list[str]):
+        """many queued requests (one directory each: cloud.data + operator.txt) as one batch on the GPU; every
+        directory gets its answer.data; returns the exit code ./cloud would have had in each"""
+        codes, _ = self.session.compute_dirs(directories)
+        return [int(c) for c in codes]
+
     def close(self):
         self.session.close()

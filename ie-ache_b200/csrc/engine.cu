@@ -9,6 +9,8 @@
 #include <cuda_runtime.h>
 
 #include <chrono>
+#include <thread>
+#include <atomic>
 #include <map>
 #include <cstdarg>
 #include <cstdio>
@@ -1002,6 +1004,70 @@ extern "C" int ieache_session_eval_postfix(ieache_session *s, const char *postfi
     for (size_t e = 0; e < n_expr; e++) memcpy(answers + e * blk, stack_ptr.back() + e * stack_stride.back(), blk * 4);
     if (seconds) *seconds = secs;
     return last_code;
+}
+
+/* Batched ingest: `count` request directories, each holding what ./cloud reads (cloud.data =
+ * two 352-record client blocks, operator.txt), evaluated as ONE levelised batch with the session's keys; every
+ * directory gets the answer.data (and, on multiply, the averagestandard.txt line) ./cloud would have written.
+ * Files are parsed and written by a small pool of host threads; the circuit time is shared by all requests of a
+ * group, so `seconds` is the time of the whole batch.  exit_codes[i] = 0 / 126 like ./cloud, or a negative
+ * IEACHE_ERR_* when that directory could not be read or written (the others still run). */
+extern "C" int ieache_session_compute_dirs(ieache_session *s, size_t count, const char *const *dirs, int32_t *exit_codes, double *seconds)
+{
+    if (!s || !dirs || !exit_codes) return fail(IEACHE_ERR_ARG, "null argument");
+    if (seconds) *seconds = 0;
+    if (count == 0) return IEACHE_OK;
+    const int n = s->key->p.n;
+    const size_t w = n + 1, blk = 352 * w;
+    std::vector<int32_t> o1(count * blk), o2(count * blk), answers(count * blk), ops(count, 0), codes(count, 0);
+    std::vector<size_t> counts(count, 0);
+    std::vector<int> io_err(count, 0);
+    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    auto parallel = [&](auto &&fn) {
+        std::vector<std::thread> pool;
+        std::atomic<size_t> next{0};
+        for (unsigned t = 0; t < std::min<size_t>(hw, count); t++)
+            pool.emplace_back([&] { for (size_t i; (i = next.fetch_add(1)) < count;) fn(i); });
+        for (auto &th : pool) th.join();
+    };
+    parallel([&](size_t i) {
+        const std::string d(dirs[i] ? dirs[i] : "");
+        std::vector<int32_t> data(704 * w);
+        FILE *f = fopen((d + "/cloud.data").c_str(), "rb");
+        if (!f) { io_err[i] = IEACHE_ERR_IO; return; }
+        const int rc = read_samples(f, n, data.data(), 704);
+        fclose(f);
+        if (rc) { io_err[i] = rc; return; }
+        memcpy(&o1[i * blk], data.data(), blk * 4);
+        memcpy(&o2[i * blk], data.data() + blk, blk * 4);
+        int op = 0;
+        f = fopen((d + "/operator.txt").c_str(), "r");
+        if (!f) { io_err[i] = IEACHE_ERR_IO; return; }
+        if (fscanf(f, "%d", &op) != 1) op = 0;
+        fclose(f);
+        ops[i] = op;
+    });
+    /* unreadable directories are left out of the batch (operator 0 selects no circuit, cloud.c computes nothing) */
+    for (size_t i = 0; i < count; i++) if (io_err[i]) ops[i] = 0;
+    double secs = 0;
+    const int rc = ieache_session_compute_batch(s, count, ops.data(), o1.data(), o2.data(), answers.data(), codes.data(), counts.data(), &secs);
+    if (rc) return rc;
+    const double var = s->key->p.ks_stdev * s->key->p.ks_stdev;
+    parallel([&](size_t i) {
+        if (io_err[i]) { exit_codes[i] = io_err[i]; return; }
+        exit_codes[i] = codes[i];
+        const std::string d(dirs[i]);
+        if (counts[i] == 352 && ops[i] == 4) {                                   /* cloud.c:2468-2471 */
+            FILE *t = fopen((d + "/averagestandard.txt").c_str(), "a");
+            if (t) { fprintf(t, "%lf\n", secs); fclose(t); }
+        }
+        FILE *f = fopen((d + "/answer.data").c_str(), "wb");
+        if (!f) { exit_codes[i] = IEACHE_ERR_IO; return; }
+        if (write_samples(f, n, &answers[i * blk], counts[i], var)) exit_codes[i] = IEACHE_ERR_IO;
+        fclose(f);
+    });
+    if (seconds) *seconds = secs;
+    return IEACHE_OK;
 }
 
 extern "C" int ieache_cloud_run(ieache_ctx *ctx, const char *dir, double *seconds)

@@ -211,6 +211,11 @@ int ieache_session_compute_batch(ieache_session *s, size_t count, const int32_t 
  * answer.data -> cloud.data round trips; operands: [n_expr][n_operands][352][n+1] */
 int ieache_session_eval_postfix(ieache_session *s, const char *postfix, size_t n_expr, const int32_t *operands,
                                 int n_operands, int32_t *answers, size_t *answer_counts, double *seconds);
+/* Batched ingest (replaces `count` runs of ./cloud, Cloud/dragonfly_cipher_cloud.py:1233): every dirs[i] holds
+ * cloud.data (2 x 352 records) and operator.txt; all requests are evaluated as one levelised batch and every
+ * directory receives its answer.data (plus the averagestandard.txt line on multiply).  exit_codes[i] = 0 / 126 as
+ * ./cloud would exit, or a negative IEACHE_ERR_* if that directory could not be read or written. */
+int ieache_session_compute_dirs(ieache_session *s, size_t count, const char *const *dirs, int32_t *exit_codes, double *seconds);
 
 #ifdef __cplusplus
 }

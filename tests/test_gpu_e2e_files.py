@@ -42,3 +42,34 @@ def test_keygen_alice_cloud_verif_default_parameters(tmp_path, pkg, oracle):
     rc, _ = eng.cloud_run(d)
     assert rc == 126 and os.path.getsize(os.path.join(d, "answer.data")) == 162304
     ks.free(); nbit.free(); eng.close()
+
+
+def test_batched_ingest_of_request_directories(tmp_path, pkg):
+    """several Cloud request directories (cloud.data + operator.txt) evaluated as one batch; each
+    gets the answer.data ./cloud would have written (decoded by the verifier), unreadable ones are reported"""
+    import shutil
+    keys = str(tmp_path / "keys")
+    os.makedirs(keys)
+    eng = pkg.Engine(0)
+    eng.keygen_files(keys, pkg.Params.default(16))                   # small LWE dimension: the circuits are the point here
+    cases = [(1, 0, 1000, 0, 234), (2, 0, 1000, 0, 234), (4, 0, 77, 0, 1001), (1, 2, 5, 0, 9), (2, 0, 3, 0, 10), (4, 2, 12, 0, 12)]
+    want = [{1: va + vb, 2: va - vb, 4: va * vb}[op] for op, s1, a, s2, b in cases for va, vb in [(-a if s1 == 2 else a, -b if s2 == 2 else b)]]
+    dirs = []
+    for k, (op, s1, v1, s2, v2) in enumerate(cases):
+        d = str(tmp_path / f"req{k}")
+        os.makedirs(d)
+        for f in ("secret.key", "nbit.key"):
+            shutil.copy(os.path.join(keys, f), d)                    # the verifier's and alice's keys
+        pkg.alice_encrypt(d, s1, 32, v1, os.path.join(d, "cloud.data"))
+        pkg.alice_encrypt(d, s2, 32, v2, os.path.join(d, "cloud.data"), append=True)
+        open(os.path.join(d, "operator.txt"), "w").write(str(op))
+        dirs.append(d)
+    dirs.append(str(tmp_path / "missing"))
+    sess = eng.session(os.path.join(keys, "cloud.key"), os.path.join(keys, "nbit.key"))
+    codes, secs = sess.compute_dirs(dirs)
+    assert list(codes[:-1]) == [0] * len(cases) and codes[-1] == -3 and secs > 0      # IEACHE_ERR_IO for the missing directory
+    for d, (op, *_), w in zip(dirs, cases, want):
+        assert os.path.getsize(os.path.join(d, "answer.data")) == 352 * (4 + 17 * 4 + 8)
+        value, code, width = pkg.verif_run(d)
+        assert value == w and width == (64 if op == 4 else 32), (d, value, code, width, w)
+    sess.close(); eng.close()
