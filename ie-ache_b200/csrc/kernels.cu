@@ -135,15 +135,6 @@ blind_rotate_kernel(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga,
 {
     blind_rotate_body<L, G, MINB, ROLL, NOBK, LOCK, SPREAD, ACCREG>(p, bkfft, ga, baseA, baseB, ext);
 }
-/* same body with an explicit register cap (5 CTAs of 64 threads per SM at 200 registers) */
-template <int L>
-__global__ void __maxnreg__(200)
-blind_rotate_kernel_r200(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
-                         const int32_t *__restrict__ baseB, int32_t *__restrict__ ext)
-{
-    blind_rotate_body<L, 1, 5, 0, false, false>(p, bkfft, ga, baseA, baseB, ext);
-}
-
 template <int L, int G, int MINB, int ROLL, int NOBK, bool LOCK, bool SPREAD, bool ACCREG>
 __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
                     const int32_t *__restrict__ baseB, int32_t *__restrict__ ext)
@@ -311,122 +302,11 @@ __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__
     if (tid == 0) o[kN] = acc[kN];
 }
 
-/* ---- latency variant: one gate per CTA, one 64-thread group per forward transform ----
- * A circuit level of one expression holds ~45 gates: far too few to fill 148 SMs with the
- * throughput kernel, so the level time is one gate's latency.  Here the (k+1)l = 2L forward transforms of a
- * CMux step run in parallel on 2L groups; every group writes its two partial products (one per output
- * polynomial) into its own exchange buffers; groups 0 and 1 then sum the 2L partials of "their" polynomial,
- * run the inverse transform and update ACC.  Two CTA barriers per step. */
-constexpr int kWideInvBytes = 2 * kBufBytes; /* private exchange buffers of the two inverse transforms */
-constexpr int wide_smem_bytes(int L) { return kAccBytes + 2 * L * 2 * kBufBytes + kWideInvBytes + kAbarBytes; }
-
-template <int L>
-__global__ void __launch_bounds__(64 * 2 * L, 1)
-blind_rotate_wide_kernel(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
-                         const int32_t *__restrict__ baseB, int32_t *__restrict__ ext)
-{
-    constexpr int NG = 2 * L, NT = 64 * NG;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int grp = threadIdx.x >> 6, tid = threadIdx.x & 63;
-    const int g = blockIdx.x;
-    int32_t *acc = reinterpret_cast<int32_t *>(smem_raw);
-    cd *bufs = reinterpret_cast<cd *>(smem_raw + kAccBytes);                 /* [NG][2][576] */
-    cd *invbuf = reinterpret_cast<cd *>(smem_raw + kAccBytes + NG * 2 * kBufBytes) + (grp & 1) * kBufElems;
-    uint16_t *abar = reinterpret_cast<uint16_t *>(smem_raw + kAccBytes + NG * 2 * kBufBytes + kWideInvBytes);
-    cd *myA = bufs + (size_t)grp * 2 * kBufElems, *myB = myA + kBufElems;
-
-    const int n = p.n;
-    {
-        const int e = g / ga.ntempl, t = g - e * ga.ntempl;
-        GateT gt = ga.uni;
-        if (ga.tmpl) gt = ga.tmpl[t]; else { gt.in0 = (gt.in0 >= 0) ? t : -1; gt.in1 = (gt.in1 >= 0) ? t : -1; }
-        const size_t blk = (size_t)e * ga.inst_samples;
-        const int32_t *in0 = gt.in0 >= 0 ? baseA + (blk + gt.in0) * ga.stride : nullptr;
-        const int32_t *in1 = gt.in1 >= 0 ? baseB + (blk + gt.in1) * ga.stride : nullptr;
-        const int32_t c0 = gt.c0, c1 = gt.c1, cst = gt.cst_mu * p.mu;
-        for (int i = threadIdx.x; i <= n; i += NT) {
-            int32_t v = (i == n) ? cst : 0;
-            if (in0) v += c0 * __ldg(in0 + i);
-            if (in1) v += c1 * __ldg(in1 + i);
-            abar[i] = (uint16_t)modswitch_2N(v);
-        }
-    }
-    __syncthreads();
-    {
-        const int bbar = abar[n];
-        const int a = (2 * kN - bbar) & (2 * kN - 1), ar = a & (kN - 1);
-        const bool flip = a >= kN;
-        for (int j = threadIdx.x; j < kN; j += NT) { acc[j] = 0; acc[kN + j] = ((j < ar) != flip) ? -p.mu : p.mu; }
-    }
-    __syncthreads();
-
-    const Tw w1 = tw_pass1(), w2 = d_tw2[tid >> 3], w3 = d_tw3[tid];
-    const int Bgbit = p.Bgbit;
-    const uint32_t maskBg = (1u << Bgbit) - 1;
-    const int32_t halfBg = 1 << (Bgbit - 1);
-    uint32_t offset = 0;
-#pragma unroll
-    for (int i = 1; i <= L; i++) offset += (uint32_t)halfBg << (32 - i * Bgbit);
-    const int q = grp / L, pp = grp % L, shift = 32 - (pp + 1) * Bgbit;
-    constexpr int kRowElems = 2 * kHalfN, kBkStride = 2 * L * kRowElems;
-
-    for (int i = 0; i < n; i++) {
-        const int a = abar[i];
-        if (a == 0) continue; /* uniform in the CTA */
-        {
-            int32_t c[16];
-            rot_minus_one(acc + q * kN, tid, a, c);
-            double xr[8], xi[8];
-#pragma unroll
-            for (int m = 0; m < 8; m++) {
-                xr[m] = digit_f64(c[m], offset, shift, maskBg, halfBg);
-                xi[m] = digit_f64(c[8 + m], offset, shift, maskBg, halfBg);
-            }
-            fwd_transform(xr, xi, myA, tid, grp, w1, w2, w3);
-            const double2 *bk_r = bkfft + (size_t)i * kBkStride + (size_t)grp * kRowElems + tid;
-            double2 b0[8], b1[8];
-#pragma unroll
-            for (int r = 0; r < 8; r++) { b0[r] = __ldg(bk_r + r * 64); b1[r] = __ldg(bk_r + kHalfN + r * 64); }
-            group_sync(grp); /* every thread of the group has finished reading myA in pass 3 */
-#pragma unroll
-            for (int r = 0; r < 8; r++) {
-                cd v0, v1;
-                v0.x = xr[r] * b0[r].x - xi[r] * b0[r].y; v0.y = xr[r] * b0[r].y + xi[r] * b0[r].x;
-                v1.x = xr[r] * b1[r].x - xi[r] * b1[r].y; v1.y = xr[r] * b1[r].y + xi[r] * b1[r].x;
-                myA[r * 64 + tid] = v0;
-                myB[r * 64 + tid] = v1;
-            }
-        }
-        __syncthreads();
-        if (grp < 2) {
-            double sr[8], si[8];
-#pragma unroll
-            for (int r = 0; r < 8; r++) { sr[r] = 0.0; si[r] = 0.0; }
-            const cd *src = bufs + (size_t)grp * kBufElems + tid; /* bufA of group 0 for j = 0, bufB for j = 1 */
-#pragma unroll
-            for (int gg = 0; gg < NG; gg++)
-#pragma unroll
-                for (int r = 0; r < 8; r++) { const cd v = src[(size_t)gg * 2 * kBufElems + r * 64]; sr[r] += v.x; si[r] += v.y; }
-            inv_transform(sr, si, invbuf, tid, grp, w1, w2, w3);
-            int32_t *accj = acc + grp * kN;
-#pragma unroll
-            for (int m = 0; m < 8; m++) {
-                accj[tid + 64 * m] += round_to_torus(sr[m]);
-                accj[tid + 64 * m + 512] += round_to_torus(si[m]);
-            }
-        }
-        __syncthreads();
-    }
-    int32_t *o = ext + (size_t)g * kExtStride;
-    for (int j = threadIdx.x; j < kN; j += NT) o[j] = (j == 0) ? acc[0] : -acc[kN - j];
-    if (threadIdx.x == 0) o[kN] = acc[kN];
-}
-
 /* ---- latency variant with two groups per gate: group q owns ACC polynomial q, runs its l forward transforms
  * with register accumulators for both output polynomials, hands the partial sum of the *other* polynomial to
  * the other group through 8 KB of shared memory, and inverts / updates its own polynomial.  Per step: 4
- * transform latencies instead of 8, and only 32 KB of extra shared-memory traffic (the 2l-group kernel above
- * moves 192 KB and is LSU-bound at 72 %: profiles/README.md). */
+ * transform latencies instead of 8, and only 32 KB of extra shared-memory traffic (an earlier kernel with one
+ * group per forward transform moved 192 KB per step and was LSU-bound at 72 %). */
 constexpr int pair_smem_bytes() { return kAccBytes + 2 * 2 * kBufBytes + 2 * kHalfN * 16 + kAbarBytes; }
 
 template <int L, int MINB = 2>
@@ -790,17 +670,6 @@ static long long g_cluster_max = [] { const char *e = getenv("IEACHE_CLUSTER_MAX
 void set_cluster_max(long long v) { g_cluster_max = v; }
 long long get_cluster_max() { return g_cluster_max; }
 
-template <int L>
-static cudaError_t launch_br_wide(const DevParams &p, const double2 *bkfft, const GateAddr &ga, const int32_t *baseA,
-                                  const int32_t *baseB, int32_t *ext, long long count, cudaStream_t s)
-{
-    constexpr int smem = wide_smem_bytes(L);
-    cudaError_t e = cudaFuncSetAttribute(blind_rotate_wide_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    blind_rotate_wide_kernel<L><<<(int)count, 64 * 2 * L, smem, s>>>(p, bkfft, ga, baseA, baseB, ext);
-    return cudaGetLastError();
-}
-
 /* launch configuration: IEACHE_BR_VARIANT selects among the compiled variants (tuning aid) */
 static int br_variant()
 {
@@ -845,14 +714,8 @@ cudaError_t launch_blind_rotate(const DevParams &p, const double2 *bkfft, const 
         two_group = count * 10 < waves * slots * 9;
     }
     if (two_group) {
-        static const int lat = [] { const char *e = getenv("IEACHE_LATENCY_KERNEL"); return e ? atoi(e) : 2; }();
-        if (lat == 6) {
-            if (p.l == 3) return launch_br_wide<3>(p, bkfft, ga, baseA, baseB, ext, count, s);
-            if (p.l == 2) return launch_br_wide<2>(p, bkfft, ga, baseA, baseB, ext, count, s);
-        } else {
-            if (p.l == 3) return launch_br_pair<3>(p, bkfft, ga, baseA, baseB, ext, count, s);
-            if (p.l == 2) return launch_br_pair<2>(p, bkfft, ga, baseA, baseB, ext, count, s);
-        }
+        if (p.l == 3) return launch_br_pair<3>(p, bkfft, ga, baseA, baseB, ext, count, s);
+        if (p.l == 2) return launch_br_pair<2>(p, bkfft, ga, baseA, baseB, ext, count, s);
     }
     if (p.l == 2) return launch_br_variant<2, 1, 4, 2>(p, bkfft, ga, baseA, baseB, ext, count, s);
     if (p.l != 3) return cudaErrorInvalidValue;
@@ -866,12 +729,6 @@ cudaError_t launch_blind_rotate(const DevParams &p, const double2 *bkfft, const 
     case 8: return launch_br_variant<3, 1, 5, 0>(p, bkfft, ga, baseA, baseB, ext, count, s);
     case 9: return launch_br_variant<3, 1, 6, 0>(p, bkfft, ga, baseA, baseB, ext, count, s);
     case 10: return launch_br_variant<3, 1, 5, 1>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 20: {
-        cudaError_t e = cudaFuncSetAttribute(blind_rotate_kernel_r200<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGroupSmem);
-        if (e != cudaSuccess) return e;
-        blind_rotate_kernel_r200<3><<<(int)count, 64, kGroupSmem, s>>>(p, bkfft, ga, baseA, baseB, ext);
-        return cudaGetLastError();
-    }
     case 21: return launch_br_variant<3, 1, 6, 2>(p, bkfft, ga, baseA, baseB, ext, count, s);
     case 22: return launch_br_variant<3, 1, 6, 3>(p, bkfft, ga, baseA, baseB, ext, count, s);
     case 24: return launch_br_variant<3, 1, 4, 3>(p, bkfft, ga, baseA, baseB, ext, count, s);

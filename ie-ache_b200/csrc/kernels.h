@@ -76,7 +76,7 @@ cudaError_t launch_circuit_gather_outputs(int32_t *outputs, const int32_t *wires
 /* dense FP64 FMA microbenchmark (best of 3), TFLOP/s */
 cudaError_t launch_fp64_peak(cudaStream_t s, double *tflops);
 
-/* launches with <= wide_max gates use the latency kernel (one gate per CTA, 2l groups) */
+/* launches with <= wide_max gates use the two-group latency kernel (one gate per CTA, one group per ACC polynomial) */
 void set_wide_max(long long v);
 long long get_wide_max();
 /* launches with <= cluster_max gates (and <= wide_max) use the 2-CTA-cluster latency kernel (one gate on two SMs) */

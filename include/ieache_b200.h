@@ -66,9 +66,10 @@ int ieache_ctx_kernel_times(ieache_ctx *ctx, double *blind_rotate_ms, double *ke
                             uint64_t *blind_rotate_launches, uint64_t *keyswitch_launches, int reset);
 int ieache_ctx_set_timing(ieache_ctx *ctx, int enabled);
 
-/* Kernel selection: launches of at most `max_gates` gates use the latency variant of the blind rotation
- * (one gate per CTA, one thread group per forward transform), larger ones the throughput variant.
- * Process-wide; returns the previous value; a negative argument only queries.  Default 296 (two waves of one-gate CTAs on 148 SMs). */
+/* Kernel selection: launches of at most `max_gates` gates use the two-group latency variant of the blind rotation
+ * (one gate per CTA, one thread group per accumulator polynomial), larger ones the throughput variant unless its
+ * last wave of 4 x SMs gates would be less than 90 % full.  0 forces the throughput variant for every size.
+ * Process-wide; returns the previous value; a negative argument only queries.  Default 296 (one wave of two CTAs per SM). */
 int64_t ieache_set_wide_max(int64_t max_gates);
 /* Launches of at most max_gates gates (and at most the limit above) use the cluster latency kernel: one gate on a
  * pair of SMs (thread-block cluster of 2, products exchanged through distributed shared memory).  Same calling
