@@ -706,7 +706,7 @@ cudaError_t launch_blind_rotate(const DevParams &p, const double2 *bkfft, const 
     /* The throughput kernel holds 4 gates per SM, so its time moves in steps of 4 x SMs gates (592: 5.8 ms, 720:
      * 9.3 ms); the two-group kernel holds 2 gates per SM at 97 % of the throughput kernel's full-wave rate and
      * finer steps (720 gates: 7.4 ms).  Launches that would leave more than 10 % of the throughput kernel's last
-     * wave empty therefore also use it (measured table in DESIGN.md 4.2). */
+     * wave empty therefore also use it (measured table in DESIGN.md 4). */
     bool two_group = count <= g_wide_max;
     if (!two_group && g_wide_max > 0) {
         static const long long slots = [] { int d = 0, sms = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d); return 4LL * sms; }();
