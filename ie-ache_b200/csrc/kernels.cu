@@ -47,6 +47,7 @@ cudaError_t twiddle_ptrs(const Tw **tw2, const Tw **tw3)
 /* named barrier of one 64-thread group.  With one group per CTA the id is a compile-time constant (ptxas then
  * reserves 2 barriers instead of 16, worth ~5 % in the throughput kernel); a switch over immediate ids was
  * measured slower than the register form for the multi-group kernels. */
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 constexpr int kCtaBarrier = -1; /* group id meaning "the gate's threads are spread over every warp of the CTA" */
 __device__ __forceinline__ void group_sync(int grp)
 {
@@ -302,6 +303,200 @@ __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__
     if (tid == 0) o[kN] = acc[kN];
 }
 
+/* ---- throughput variant with the transform-domain accumulators in tensor memory ----
+ * The 784 LSU wavefronts a gate-step spends on BK_i are per gate because a thread has no registers left to serve a
+ * second gate: 64 of its 252 registers are accumulators.  Here they live in TMEM (tcgen05.st / tcgen05.ld, 32x32b:
+ * every thread owns its lane's columns; ~5 KB/clk/SM of read bandwidth measured by tools/tmem_probe.cu), one
+ * 64-thread group owns GP gates, and each BK_i row is loaded into registers once and used for the GP forward
+ * transforms of that row: BK wavefronts and L1/L2 traffic per gate drop by GP.
+ * CTA = one 64-thread group (TMEM lanes 0..63), 4 CTAs per SM, GP * 64 columns per CTA (512 in all at GP = 2). */
+template <int GP> __host__ __device__ constexpr int tmem_group_smem() { return GP * (kAccBytes + kAbarBytes) + 2 * kBufBytes; }
+
+/* 32 columns = 16 doubles per thread (one polynomial's 8 slots x {re, im}); the b32 halves are packed inside the asm
+ * so that ptxas allocates them as the register pairs of the doubles (no move instructions) */
+#define IE_TMEM_LD16D(taddr, d) asm volatile("{\n\t.reg .b32 t<32>;\n\t" \
+    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {t0,t1,t2,t3,t4,t5,t6,t7,t8,t9,t10,t11,t12,t13,t14,t15,t16,t17,t18,t19,t20,t21,t22,t23,t24,t25,t26,t27,t28,t29,t30,t31}, [%16];\n\t" \
+    "tcgen05.wait::ld.sync.aligned;\n\t" \
+    "mov.b64 %0, {t0,t1};\n\tmov.b64 %1, {t2,t3};\n\tmov.b64 %2, {t4,t5};\n\tmov.b64 %3, {t6,t7};\n\tmov.b64 %4, {t8,t9};\n\tmov.b64 %5, {t10,t11};\n\tmov.b64 %6, {t12,t13};\n\tmov.b64 %7, {t14,t15};\n\tmov.b64 %8, {t16,t17};\n\tmov.b64 %9, {t18,t19};\n\tmov.b64 %10, {t20,t21};\n\tmov.b64 %11, {t22,t23};\n\tmov.b64 %12, {t24,t25};\n\tmov.b64 %13, {t26,t27};\n\tmov.b64 %14, {t28,t29};\n\tmov.b64 %15, {t30,t31};\n\t}" \
+    : "=d"(d[0]),"=d"(d[1]),"=d"(d[2]),"=d"(d[3]),"=d"(d[4]),"=d"(d[5]),"=d"(d[6]),"=d"(d[7]),"=d"(d[8]),"=d"(d[9]),"=d"(d[10]),"=d"(d[11]),"=d"(d[12]),"=d"(d[13]),"=d"(d[14]),"=d"(d[15]) : "r"(taddr) : "memory")
+#define IE_TMEM_ST16D(taddr, d) asm volatile("{\n\t.reg .b32 t<32>;\n\t" \
+    "mov.b64 {t0,t1}, %1;\n\tmov.b64 {t2,t3}, %2;\n\tmov.b64 {t4,t5}, %3;\n\tmov.b64 {t6,t7}, %4;\n\tmov.b64 {t8,t9}, %5;\n\tmov.b64 {t10,t11}, %6;\n\tmov.b64 {t12,t13}, %7;\n\tmov.b64 {t14,t15}, %8;\n\tmov.b64 {t16,t17}, %9;\n\tmov.b64 {t18,t19}, %10;\n\tmov.b64 {t20,t21}, %11;\n\tmov.b64 {t22,t23}, %12;\n\tmov.b64 {t24,t25}, %13;\n\tmov.b64 {t26,t27}, %14;\n\tmov.b64 {t28,t29}, %15;\n\tmov.b64 {t30,t31}, %16;\n\t" \
+    "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {t0,t1,t2,t3,t4,t5,t6,t7,t8,t9,t10,t11,t12,t13,t14,t15,t16,t17,t18,t19,t20,t21,t22,t23,t24,t25,t26,t27,t28,t29,t30,t31};\n\t}" \
+    :: "r"(taddr), "d"(d[0]),"d"(d[1]),"d"(d[2]),"d"(d[3]),"d"(d[4]),"d"(d[5]),"d"(d[6]),"d"(d[7]),"d"(d[8]),"d"(d[9]),"d"(d[10]),"d"(d[11]),"d"(d[12]),"d"(d[13]),"d"(d[14]),"d"(d[15]) : "memory")
+
+template <int L, int GP, int MINB = 4>
+__global__ void __launch_bounds__(64, MINB)
+blind_rotate_tmem_kernel(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
+                         const int32_t *__restrict__ baseB, int32_t *__restrict__ ext)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t tmem_base_slot;
+    constexpr int kCols = GP * 64;                        /* per thread: GP gates x 2 polynomials x 8 slots x 4 words */
+    constexpr int grp = 0;                                /* one group per CTA: compile-time barrier id */
+    const int tid = threadIdx.x, warp = threadIdx.x >> 5;
+    unsigned char *base = smem_raw;
+    int32_t *acc = reinterpret_cast<int32_t *>(base);                                    /* [GP][2][1024] */
+    uint16_t *abar = reinterpret_cast<uint16_t *>(base + GP * kAccBytes);                /* [GP][1040] */
+    cd *bufA = reinterpret_cast<cd *>(base + GP * (kAccBytes + kAbarBytes)), *bufB = bufA + kBufElems;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "n"(kCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    const int n = p.n;
+    const long long total = (long long)ga.ntempl * ga.n_inst;
+    const long long g_first = (long long)blockIdx.x * GP;
+    /* 1. linear pre-combination + modSwitch, 2. ACC init, for the GP gates of this group (idle slots shadow the last gate) */
+#pragma unroll
+    for (int k = 0; k < GP; k++) {
+        long long g = g_first + k;
+        if (g >= total) g = total - 1;
+        const int e = (int)(g / ga.ntempl), t = (int)(g - (long long)e * ga.ntempl);
+        GateT gt = ga.uni;
+        if (ga.tmpl) gt = ga.tmpl[t]; else { gt.in0 = (gt.in0 >= 0) ? t : -1; gt.in1 = (gt.in1 >= 0) ? t : -1; }
+        const size_t blk = (size_t)e * ga.inst_samples;
+        const int32_t *in0 = gt.in0 >= 0 ? baseA + (blk + gt.in0) * ga.stride : nullptr;
+        const int32_t *in1 = gt.in1 >= 0 ? baseB + (blk + gt.in1) * ga.stride : nullptr;
+        const int32_t c0 = gt.c0, c1 = gt.c1, cst = gt.cst_mu * p.mu;
+        for (int i = tid; i <= n; i += 64) {
+            int32_t v = (i == n) ? cst : 0;
+            if (in0) v += c0 * __ldg(in0 + i);
+            if (in1) v += c1 * __ldg(in1 + i);
+            abar[k * 1040 + i] = (uint16_t)modswitch_2N(v);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t taddr = tmem_base_slot + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+    for (int k = 0; k < GP; k++) {
+        const int bbar = abar[k * 1040 + n];
+        const int a = (2 * kN - bbar) & (2 * kN - 1), ar = a & (kN - 1);
+        const bool flip = a >= kN;
+        for (int j = tid; j < kN; j += 64) {
+            acc[k * 2 * kN + j] = 0;
+            acc[k * 2 * kN + kN + j] = ((j < ar) != flip) ? -p.mu : p.mu;
+        }
+    }
+    group_sync(grp);
+
+    const Tw w1 = tw_pass1(), w2 = d_tw2[tid >> 3], w3 = d_tw3[tid];
+    const int Bgbit = p.Bgbit;
+    const uint32_t maskBg = (1u << Bgbit) - 1;
+    const int32_t halfBg = 1 << (Bgbit - 1);
+    uint32_t offset = 0;
+#pragma unroll
+    for (int i = 1; i <= L; i++) offset += (uint32_t)halfBg << (32 - i * Bgbit);
+    constexpr int kRowElems = 2 * kHalfN, kBkStride = 2 * L * kRowElems;
+    int toggle = 0;
+
+    for (int i = 0; i < n; i++) {
+        const double2 *bk_r = bkfft + (size_t)i * kBkStride + tid;
+#pragma unroll 1
+        for (int q = 0; q < 2; q++) {
+            int32_t c[GP][16];
+#pragma unroll
+            for (int k = 0; k < GP; k++) rot_minus_one(acc + (k * 2 + q) * kN, tid, abar[k * 1040 + i], c[k]);
+#pragma unroll 1
+            for (int pp = 0; pp < L; pp++) {
+                const int shift = 32 - (pp + 1) * Bgbit;
+                /* this row of BK_i: once for the GP gates of the group.  With more than 4 CTAs per SM there are no
+                 * registers to hold it across a transform: it is then requested per polynomial right before use */
+                double2 b0[8], b1[8];
+                if (MINB <= 4) {
+#pragma unroll
+                    for (int r = 0; r < 8; r++) { b0[r] = __ldg(bk_r + r * 64); b1[r] = __ldg(bk_r + kHalfN + r * 64); }
+                }
+                const double2 *bk_row = bk_r;
+                bk_r += kRowElems;
+                const bool first = (q == 0) && (pp == 0);
+#pragma unroll
+                for (int k = 0; k < GP; k++) {
+                    double xr[8], xi[8];
+#pragma unroll
+                    for (int m = 0; m < 8; m++) {
+                        xr[m] = digit_f64(c[k][m], offset, shift, maskBg, halfBg);
+                        xi[m] = digit_f64(c[k][8 + m], offset, shift, maskBg, halfBg);
+                    }
+                    cd *buf = toggle ? bufB : bufA;
+                    toggle ^= 1;
+                    fwd_transform(xr, xi, buf, tid, grp, w1, w2, w3);
+                    /* accumulate into TMEM (layout per gate and polynomial: 8 slots x {re, im}), one output polynomial
+                     * at a time; stores of the previous row to the same columns are long complete, the wait only
+                     * orders them */
+                    if (!first) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        double sacc[16];
+                        const uint32_t tj = taddr + (uint32_t)((k * 2 + j) * 32);
+                        double2 bj[8];
+#pragma unroll
+                        for (int r = 0; r < 8; r++) bj[r] = (MINB <= 4) ? (j ? b1[r] : b0[r]) : __ldg(bk_row + j * kHalfN + r * 64);
+                        if (!first) {
+                            IE_TMEM_LD16D(tj, sacc);
+                        } else {
+#pragma unroll
+                            for (int r = 0; r < 16; r++) sacc[r] = 0.0;
+                        }
+#pragma unroll
+                        for (int r = 0; r < 8; r++) cmac(sacc[2 * r], sacc[2 * r + 1], xr[r], xi[r], bj[r].x, bj[r].y);
+                        IE_TMEM_ST16D(tj, sacc);
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        /* inverse transforms and ACC update */
+#pragma unroll 1
+        for (int kj = 0; kj < 2 * GP; kj++) {
+            double sv[16];
+            const uint32_t t0 = taddr + (uint32_t)(kj * 32);
+            IE_TMEM_LD16D(t0, sv);
+            double sr[8], si[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) { sr[r] = sv[2 * r]; si[r] = sv[2 * r + 1]; }
+            cd *buf = toggle ? bufB : bufA;
+            toggle ^= 1;
+            inv_transform(sr, si, buf, tid, grp, w1, w2, w3);
+            int32_t *accj = acc + (size_t)kj * kN;
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                accj[tid + 64 * m] += round_to_torus(sr[m]);
+                accj[tid + 64 * m + 512] += round_to_torus(si[m]);
+            }
+        }
+        group_sync(grp);
+    }
+
+    /* SampleExtract */
+#pragma unroll
+    for (int k = 0; k < GP; k++) {
+        const long long g = g_first + k;
+        if (g < total) {
+            int32_t *o = ext + (size_t)g * kExtStride;
+            const int32_t *ak = acc + k * 2 * kN;
+            for (int j = tid; j < kN; j += 64) o[j] = (j == 0) ? ak[0] : -ak[kN - j];
+            if (tid == 0) o[kN] = ak[kN];
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_slot), "n"(kCols));
+}
+
+template <int L, int GP, int MINB = 4>
+static cudaError_t launch_br_tmem(const DevParams &p, const double2 *bkfft, const GateAddr &ga, const int32_t *baseA,
+                                  const int32_t *baseB, int32_t *ext, long long count, cudaStream_t s)
+{
+    constexpr int smem = tmem_group_smem<GP>();
+    cudaError_t e = cudaFuncSetAttribute(blind_rotate_tmem_kernel<L, GP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    const int grid = (int)((count + GP - 1) / GP);
+    blind_rotate_tmem_kernel<L, GP, MINB><<<grid, 64, smem, s>>>(p, bkfft, ga, baseA, baseB, ext);
+    return cudaGetLastError();
+}
+
 /* ---- latency variant with two groups per gate: group q owns ACC polynomial q, runs its l forward transforms
  * with register accumulators for both output polynomials, hands the partial sum of the *other* polynomial to
  * the other group through 8 KB of shared memory, and inverts / updates its own polynomial.  Per step: 4
@@ -439,7 +634,6 @@ __host__ __device__ constexpr int cluster_smem_bytes(int L)
            2 * L * kClPartialBytes /*received, by parity*/ + kAbarBytes + 64;
 }
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t map_to_peer(uint32_t local_addr, uint32_t rank)
 {
     uint32_t r;
@@ -720,6 +914,10 @@ cudaError_t launch_blind_rotate(const DevParams &p, const double2 *bkfft, const 
     if (p.l == 2) return launch_br_variant<2, 1, 4, 2>(p, bkfft, ga, baseA, baseB, ext, count, s);
     if (p.l != 3) return cudaErrorInvalidValue;
     switch (br_variant()) {
+    case 52: return launch_br_tmem<3, 2>(p, bkfft, ga, baseA, baseB, ext, count, s); /* accumulators in TMEM, 2 gates per group */
+    case 51: return launch_br_tmem<3, 1>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 55: return launch_br_tmem<3, 1, 5>(p, bkfft, ga, baseA, baseB, ext, count, s); /* 5 / 6 CTAs per SM: the registers the */
+    case 56: return launch_br_tmem<3, 1, 6>(p, bkfft, ga, baseA, baseB, ext, count, s); /* accumulators no longer occupy      */
     case 0: return launch_br_variant<3, 2, 2, 0>(p, bkfft, ga, baseA, baseB, ext, count, s); /* round-1 first version */
     case 2: return launch_br_variant<3, 1, 6, 1>(p, bkfft, ga, baseA, baseB, ext, count, s);
     case 3: return launch_br_variant<3, 2, 2, 1>(p, bkfft, ga, baseA, baseB, ext, count, s);
