@@ -151,6 +151,11 @@ def set_wide_max(max_gates: int) -> int:
     return lib().ieache_set_wide_max(max_gates)
 
 
+def set_throughput_variant(variant: int) -> int:
+    """Which compiled variant of the throughput blind rotation is used (41 default, 60 warp-per-gate/TMEM); returns the old one."""
+    return lib().ieache_set_throughput_variant(variant)
+
+
 def set_ks_staged_min(min_gates: int) -> int:
     """Key-switch launches of >= min_gates gates use the staged kernel; returns the previous threshold."""
     return lib().ieache_set_ks_staged_min(min_gates)

@@ -1,0 +1,210 @@
+/*
+ * br_warp.h — per-lane building blocks of the warp-per-gate blind rotation: the same negacyclic transform as
+ * br_core.h (512 complex points z_j = p_j + i p_{j+512} evaluated at psi^(4K+1), psi = exp(i pi/1024)), laid out for
+ * ONE warp with 16 points per lane, so that a transform needs one shared-memory exchange and one shuffle stage
+ * instead of two shared-memory exchanges (160 instead of 256 LSU wavefronts) and no CTA barrier.
+ *
+ *   pass 1 (registers): lane L holds z[L + 32 m], m = 0..15; radix-16 evaluation of P_L(Z) = sum_m z[L+32m] Z^m at the
+ *                       16 roots of Z^16 = i, Z_r = s1 w16^brev4(r), s1 = exp(i pi/32) (immediates)
+ *   exchange          : element r*33 + L written by lane L; lane l = 16 Lpar + k reads k*33 + Lpar + 2 m'
+ *   pass 2 (registers): radix-16 evaluation of R_Lpar(V) = sum_m' Q[Lpar+2m'][k] V^m' at the roots of V^16 = Z_k,
+ *                       base exp(i pi (1 + 4 kappa)/512), kappa = brev4(k)
+ *   final stage       : P(Y) = R_0(Y^2) +- Y R_1(Y^2) between lanes l and l^16; each lane does 8 of the 16
+ *                       butterflies (lane with Lpar computes r' = s + 8 Lpar, s = 0..7) after receiving 8 values
+ *   result            : lane l, register s (+8 for the minus root) holds evaluation
+ *                       K = brev4(k) + 16 brev4(s + 8 Lpar) + 256 sigma
+ *
+ * Everything is __host__ __device__: tests/emul runs the identical arithmetic on the CPU against the oracle.
+ * Replaces the same libtfhe code as br_core.h (tfhe_blindRotate_FFT / tGswFFTExternMulToTLwe, reached from
+ * Cloud/cloud.c:30-43).
+ */
+#ifndef IEACHE_BR_WARP_H
+#define IEACHE_BR_WARP_H
+
+#include "br_core.h"
+
+namespace ieache {
+
+constexpr int kWarpBufElems = 16 * 33; /* exchange buffer of one warp: 16 rows of 32 + 1 padding element */
+
+IE_HD int brev4(int r) { return ((r & 1) << 3) | ((r & 2) << 1) | ((r & 4) >> 1) | ((r >> 3) & 1); }
+
+/* twiddles of one radix-16 pass with base s: s^8, s^4, s^2, s^2 e^{i pi/4}, s, s e^{i pi/4}, s e^{i pi/8}, s e^{i 3pi/8} */
+struct Tw16 { double z8r, z8i, z4r, z4i, z2r, z2i, z2qr, z2qi, z1r, z1i, z1qr, z1qi, z1hr, z1hi, z1hqr, z1hqi; };
+
+/* forward radix-16 pass: x[m] natural order -> x[r] = value at the root s w16^brev4(r) */
+IE_HD void pass16_fwd(double (&xr)[16], double (&xi)[16], const Tw16 &w)
+{
+#pragma unroll
+    for (int m = 0; m < 8; m++) bf(xr[m], xi[m], xr[m + 8], xi[m + 8], w.z8r, w.z8i);
+#pragma unroll
+    for (int m = 0; m < 4; m++) bf(xr[m], xi[m], xr[m + 4], xi[m + 4], w.z4r, w.z4i);
+#pragma unroll
+    for (int m = 8; m < 12; m++) bf(xr[m], xi[m], xr[m + 4], xi[m + 4], -w.z4i, w.z4r);
+#pragma unroll
+    for (int m = 0; m < 2; m++) {
+        bf(xr[m], xi[m], xr[m + 2], xi[m + 2], w.z2r, w.z2i);
+        bf(xr[4 + m], xi[4 + m], xr[6 + m], xi[6 + m], -w.z2i, w.z2r);
+        bf(xr[8 + m], xi[8 + m], xr[10 + m], xi[10 + m], w.z2qr, w.z2qi);
+        bf(xr[12 + m], xi[12 + m], xr[14 + m], xi[14 + m], -w.z2qi, w.z2qr);
+    }
+    bf(xr[0], xi[0], xr[1], xi[1], w.z1r, w.z1i);
+    bf(xr[2], xi[2], xr[3], xi[3], -w.z1i, w.z1r);
+    bf(xr[4], xi[4], xr[5], xi[5], w.z1qr, w.z1qi);
+    bf(xr[6], xi[6], xr[7], xi[7], -w.z1qi, w.z1qr);
+    bf(xr[8], xi[8], xr[9], xi[9], w.z1hr, w.z1hi);
+    bf(xr[10], xi[10], xr[11], xi[11], -w.z1hi, w.z1hr);
+    bf(xr[12], xi[12], xr[13], xi[13], w.z1hqr, w.z1hqi);
+    bf(xr[14], xi[14], xr[15], xi[15], -w.z1hqi, w.z1hqr);
+}
+/* inverse pass (x16) */
+IE_HD void pass16_inv(double (&xr)[16], double (&xi)[16], const Tw16 &w)
+{
+    ibf(xr[0], xi[0], xr[1], xi[1], w.z1r, w.z1i);
+    ibf(xr[2], xi[2], xr[3], xi[3], -w.z1i, w.z1r);
+    ibf(xr[4], xi[4], xr[5], xi[5], w.z1qr, w.z1qi);
+    ibf(xr[6], xi[6], xr[7], xi[7], -w.z1qi, w.z1qr);
+    ibf(xr[8], xi[8], xr[9], xi[9], w.z1hr, w.z1hi);
+    ibf(xr[10], xi[10], xr[11], xi[11], -w.z1hi, w.z1hr);
+    ibf(xr[12], xi[12], xr[13], xi[13], w.z1hqr, w.z1hqi);
+    ibf(xr[14], xi[14], xr[15], xi[15], -w.z1hqi, w.z1hqr);
+#pragma unroll
+    for (int m = 0; m < 2; m++) {
+        ibf(xr[m], xi[m], xr[m + 2], xi[m + 2], w.z2r, w.z2i);
+        ibf(xr[4 + m], xi[4 + m], xr[6 + m], xi[6 + m], -w.z2i, w.z2r);
+        ibf(xr[8 + m], xi[8 + m], xr[10 + m], xi[10 + m], w.z2qr, w.z2qi);
+        ibf(xr[12 + m], xi[12 + m], xr[14 + m], xi[14 + m], -w.z2qi, w.z2qr);
+    }
+#pragma unroll
+    for (int m = 0; m < 4; m++) ibf(xr[m], xi[m], xr[m + 4], xi[m + 4], w.z4r, w.z4i);
+#pragma unroll
+    for (int m = 8; m < 12; m++) ibf(xr[m], xi[m], xr[m + 4], xi[m + 4], -w.z4i, w.z4r);
+#pragma unroll
+    for (int m = 0; m < 8; m++) ibf(xr[m], xi[m], xr[m + 8], xi[m + 8], w.z8r, w.z8i);
+}
+
+/* pass-1 twiddles, base exp(i pi/32), identical for every lane */
+IE_HD Tw16 tw16_pass1()
+{
+    Tw16 w;
+    w.z8r = 0.70710678118654752440;  w.z8i = 0.70710678118654752440;    /* exp(i pi/4)     */
+    w.z4r = 0.92387953251128675613;  w.z4i = 0.38268343236508977173;    /* exp(i pi/8)     */
+    w.z2r = 0.98078528040323044913;  w.z2i = 0.19509032201612826785;    /* exp(i pi/16)    */
+    w.z2qr = 0.55557023301960222474; w.z2qi = 0.83146961230254523708;   /* exp(i 5pi/16)   */
+    w.z1r = 0.99518472667219688624;  w.z1i = 0.09801714032956060199;    /* exp(i pi/32)    */
+    w.z1qr = 0.63439328416364549822; w.z1qi = 0.77301045336273696081;   /* exp(i 9pi/32)   */
+    w.z1hr = 0.88192126434835502971; w.z1hi = 0.47139673682599764856;   /* exp(i 5pi/32)   */
+    w.z1hqr = 0.29028467725446236764; w.z1hqi = 0.95694033573220886494; /* exp(i 13pi/32)  */
+    return w;
+}
+
+/* ---- exchange buffer moves (lane = 0..31) ---- */
+IE_HD void st16_pass1(cd *buf, int lane, const double (&xr)[16], const double (&xi)[16])
+{
+#pragma unroll
+    for (int r = 0; r < 16; r++) { cd v; v.x = xr[r]; v.y = xi[r]; buf[r * 33 + lane] = v; }
+}
+IE_HD void ld16_pass2(const cd *buf, int lane, double (&xr)[16], double (&xi)[16])
+{
+    const int base = (lane & 15) * 33 + (lane >> 4);
+#pragma unroll
+    for (int m = 0; m < 16; m++) { cd v = buf[base + 2 * m]; xr[m] = v.x; xi[m] = v.y; }
+}
+IE_HD void st16_ipass2(cd *buf, int lane, const double (&xr)[16], const double (&xi)[16])
+{
+    const int base = (lane & 15) * 33 + (lane >> 4);
+#pragma unroll
+    for (int m = 0; m < 16; m++) { cd v; v.x = xr[m]; v.y = xi[m]; buf[base + 2 * m] = v; }
+}
+IE_HD void ld16_ipass1(const cd *buf, int lane, double (&xr)[16], double (&xi)[16])
+{
+#pragma unroll
+    for (int r = 0; r < 16; r++) { cd v = buf[r * 33 + lane]; xr[r] = v.x; xi[r] = v.y; }
+}
+
+/* ---- final stage between lanes l and l^16 (forward) ---- */
+/* the 8 values a lane hands to its partner: R_1[s] from the Lpar = 1 lane, R_0[8+s] from the Lpar = 0 lane */
+IE_HD void fin_fwd_send(const double (&yr)[16], const double (&yi)[16], int lpar, double (&sr)[8], double (&si)[8])
+{
+#pragma unroll
+    for (int s = 0; s < 8; s++) { sr[s] = lpar ? yr[s] : yr[8 + s]; si[s] = lpar ? yi[s] : yi[8 + s]; }
+}
+/* butterflies r' = s + 8 Lpar with Y = exp(i phi): y[s] <- R_0 + Y R_1 (evaluation K), y[8+s] <- R_0 - Y R_1 (K + 256) */
+IE_HD void fin_fwd_apply(double (&yr)[16], double (&yi)[16], int lpar, const double (&rr)[8], const double (&ri)[8],
+                         const double (&zr)[8], const double (&zi)[8])
+{
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+        double ar = lpar ? rr[s] : yr[s], ai = lpar ? ri[s] : yi[s];
+        double br = lpar ? yr[8 + s] : rr[s], bi = lpar ? yi[8 + s] : ri[s];
+        bf(ar, ai, br, bi, zr[s], zi[s]);
+        yr[s] = ar; yi[s] = ai; yr[8 + s] = br; yi[8 + s] = bi;
+    }
+}
+/* ---- inverse of the final stage: local half, then the values to hand over, then their placement ---- */
+IE_HD void fin_inv_local(double (&xr)[16], double (&xi)[16], const double (&zr)[8], const double (&zi)[8])
+{
+#pragma unroll
+    for (int s = 0; s < 8; s++) ibf(xr[s], xi[s], xr[8 + s], xi[8 + s], zr[s], zi[s]); /* x[s] = 2 R_0[r'], x[8+s] = 2 R_1[r'] */
+}
+IE_HD void fin_inv_send(const double (&xr)[16], const double (&xi)[16], int lpar, double (&sr)[8], double (&si)[8])
+{
+#pragma unroll
+    for (int s = 0; s < 8; s++) { sr[s] = lpar ? xr[s] : xr[8 + s]; si[s] = lpar ? xi[s] : xi[8 + s]; }
+}
+IE_HD void fin_inv_place(double (&xr)[16], double (&xi)[16], int lpar, const double (&rr)[8], const double (&ri)[8])
+{
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+        if (lpar) { xr[s] = rr[s]; xi[s] = ri[s]; } else { xr[8 + s] = rr[s]; xi[8 + s] = ri[s]; }
+    }
+}
+
+/* evaluation index of register p (0..15) of lane l */
+IE_HD int warp_slot_to_K(int p, int lane)
+{
+    return brev4(lane & 15) + 16 * brev4((p & 7) + 8 * (lane >> 4)) + 256 * (p >> 3);
+}
+
+/* (X^a - 1) * ACC_q for the 32 coefficients of a lane: c[m] = coefficient lane+32m, c[16+m] = coefficient lane+32m+512 */
+IE_HD void rot_minus_one32(const int32_t *acc /*1024*/, int lane, int a, int32_t (&c)[32])
+{
+    const int t0 = lane - a;
+#pragma unroll
+    for (int h = 0; h < 32; h++) {
+        const int off = 32 * (h & 15) + 512 * (h >> 4);
+        const int t = t0 + off;
+        const int32_t v = acc[t & (kN - 1)];
+        c[h] = ((t & kN) ? -v : v) - acc[lane + off];
+    }
+}
+
+/* host-side generation of the per-lane twiddles: pass 2 (indexed by k = lane & 15) and the final stage (lane, s) */
+inline Tw16 make_tw16(long double ang)
+{
+    const long double q = 0.78539816339744830961566084581988L; /* pi/4 */
+    Tw16 w;
+    w.z8r = (double)cosl(8 * ang); w.z8i = (double)sinl(8 * ang);
+    w.z4r = (double)cosl(4 * ang); w.z4i = (double)sinl(4 * ang);
+    w.z2r = (double)cosl(2 * ang); w.z2i = (double)sinl(2 * ang);
+    w.z2qr = (double)cosl(2 * ang + q); w.z2qi = (double)sinl(2 * ang + q);
+    w.z1r = (double)cosl(ang); w.z1i = (double)sinl(ang);
+    w.z1qr = (double)cosl(ang + q); w.z1qi = (double)sinl(ang + q);
+    w.z1hr = (double)cosl(ang + q / 2); w.z1hi = (double)sinl(ang + q / 2);
+    w.z1hqr = (double)cosl(ang + 3 * q / 2); w.z1hqi = (double)sinl(ang + 3 * q / 2);
+    return w;
+}
+struct FinTw { double zr[8], zi[8]; };
+inline void host_twiddles_warp(Tw16 *tw2 /*16*/, FinTw *fin /*32*/)
+{
+    const long double pi = 3.14159265358979323846264338327950288L;
+    for (int k = 0; k < 16; k++) tw2[k] = make_tw16(pi * (1 + 4 * brev4(k)) / 512.0L);
+    for (int lane = 0; lane < 32; lane++)
+        for (int s = 0; s < 8; s++) {
+            const long double phi = pi * (1 + 4 * brev4(lane & 15) + 64 * brev4(s + 8 * (lane >> 4))) / 1024.0L;
+            fin[lane].zr[s] = (double)cosl(phi); fin[lane].zi[s] = (double)sinl(phi);
+        }
+}
+
+} // namespace ieache
+#endif

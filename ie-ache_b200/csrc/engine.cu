@@ -185,6 +185,7 @@ extern "C" int64_t ieache_set_wide_max(int64_t max_gates)
     if (max_gates >= 0) set_wide_max(max_gates);
     return old;
 }
+extern "C" int ieache_set_throughput_variant(int variant) { return set_throughput_variant(variant); }
 extern "C" int64_t ieache_set_cluster_max(int64_t max_gates)
 {
     const long long old = get_cluster_max();
@@ -244,6 +245,7 @@ struct ieache_cloudkey {
     ieache_params p{};
     DevParams dp{};
     double2 *bkfft = nullptr; size_t bkfft_bytes = 0;
+    mutable double2 *bkfft_w = nullptr;                /* warp-per-gate layout of the same values, made on first use */
     int32_t *ksk = nullptr; size_t ksk_bytes = 0;
     bool owns = true;
 };
@@ -314,11 +316,12 @@ extern "C" int ieache_cloudkey_load_file(ieache_ctx *ctx, const char *path, ieac
 extern "C" void ieache_cloudkey_destroy(ieache_cloudkey *key)
 {
     if (!key) return;
-    if (key->owns) {
+    if (key->owns || key->bkfft_w) {
         cudaSetDevice(key->ctx->device);
         cudaStreamSynchronize(key->ctx->stream);
-        cudaFree(key->bkfft); cudaFree(key->ksk);
     }
+    if (key->owns) { cudaFree(key->bkfft); cudaFree(key->ksk); }
+    cudaFree(key->bkfft_w); /* always owned: derived from bkfft on first use */
     delete key;
 }
 extern "C" int ieache_cloudkey_params(const ieache_cloudkey *key, ieache_params *out)
@@ -483,13 +486,18 @@ static int apply_l2_persist(ieache_ctx *ctx, const ieache_cloudkey *key)
 }
 
 /* ------------------------------------------------------------------ launches with optional timing */
+constexpr size_t kHalfNBytes = 512 * sizeof(double2);
 static int run_br(ieache_ctx *ctx, const ieache_cloudkey *key, const GateAddr &ga, const int32_t *A, const int32_t *B, int ext_base,
                   int32_t *ext = nullptr)
 {
     TimedLaunch t{};
     { int rcp = apply_l2_persist(ctx, key); if (rcp) return rcp; }
     if (ctx->timing) { CU(cudaEventCreate(&t.a)); CU(cudaEventCreate(&t.b)); t.kind = 0; CU(cudaEventRecord(t.a, ctx->stream)); }
-    CU(launch_blind_rotate(key->dp, key->bkfft, ga, A, B, ext ? ext : ctx->d_ext, ext_base, ctx->stream));
+    if (!key->bkfft_w && blind_rotate_uses_warp_layout((long long)ga.ntempl * ga.n_inst)) {
+        CU(cudaMalloc((void **)&key->bkfft_w, key->bkfft_bytes));
+        CU(launch_bk_relayout_warp(key->bkfft, key->bkfft_w, (int)(key->bkfft_bytes / (kHalfNBytes)), ctx->stream));
+    }
+    CU(launch_blind_rotate(key->dp, key->bkfft, key->bkfft_w, ga, A, B, ext ? ext : ctx->d_ext, ext_base, ctx->stream));
     if (ctx->timing) { CU(cudaEventRecord(t.b, ctx->stream)); ctx->timed.push_back(t); }
     ctx->launches++;
     return IEACHE_OK;

@@ -17,6 +17,7 @@
  */
 #include "kernels.h"
 #include "br_core.h"
+#include "br_warp.h"
 
 #include <cooperative_groups.h>
 #include <math.h>
@@ -27,12 +28,21 @@ namespace ieache {
 
 __device__ Tw d_tw2[8];
 __device__ Tw d_tw3[64];
+__device__ Tw16 d_tw16[16];   /* warp layout: pass-2 twiddles by lane & 15 */
+__device__ FinTw d_fin[32];   /* warp layout: final-stage twiddles by lane */
 
 cudaError_t upload_twiddles()
 {
     Tw tw2[8], tw3[64];
     host_twiddles(tw2, tw3);
     cudaError_t e = cudaMemcpyToSymbol(d_tw2, tw2, sizeof(tw2));
+    if (e != cudaSuccess) return e;
+    Tw16 tw16[16];
+    FinTw fin[32];
+    host_twiddles_warp(tw16, fin);
+    e = cudaMemcpyToSymbol(d_tw16, tw16, sizeof(tw16));
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbol(d_fin, fin, sizeof(fin));
     if (e != cudaSuccess) return e;
     return cudaMemcpyToSymbol(d_tw3, tw3, sizeof(tw3));
 }
@@ -497,6 +507,207 @@ static cudaError_t launch_br_tmem(const DevParams &p, const double2 *bkfft, cons
     return cudaGetLastError();
 }
 
+/* ---- throughput variant with one WARP per gate (br_warp.h): 16 points per lane, one shared-memory exchange and one
+ * shuffle stage per transform (160 LSU wavefronts instead of 256), no CTA barrier in the loop, accumulators in TMEM
+ * (2 polynomials x 16 slots x 4 words = 128 columns per lane).  CTA = 4 warps = 4 gates = the four lane quadrants of
+ * the CTA's 128 TMEM columns; 2 CTAs per SM.  Reads the bootstrapping key in the layout [row][poly][slot 16][lane 32]
+ * that bk_relayout_warp_kernel derives from the [slot 8][thread 64] one at key load (same values, permuted). */
+constexpr int kWarpGateSmem = kAccBytes + kWarpBufElems * 16 + kAbarBytes; /* 18 720 B per gate */
+
+__global__ void __launch_bounds__(512) bk_relayout_warp_kernel(const double2 *__restrict__ old, double2 *__restrict__ neu, int npoly)
+{
+    const int q = blockIdx.x, idx = threadIdx.x;
+    if (q >= npoly) return;
+    const int K = warp_slot_to_K(idx >> 5, idx & 31);
+    const int t3 = 8 * (K & 7) + ((K >> 3) & 7), r8 = brev3(K >> 6); /* br_core.h: K = b + 8k' + 64 brev3(r), t3 = 8b + k' */
+    neu[(size_t)q * kHalfN + idx] = old[(size_t)q * kHalfN + r8 * 64 + t3];
+}
+cudaError_t launch_bk_relayout_warp(const double2 *bkfft, double2 *bkfft_w, int npoly, cudaStream_t s)
+{
+    bk_relayout_warp_kernel<<<npoly, 512, 0, s>>>(bkfft, bkfft_w, npoly);
+    return cudaGetLastError();
+}
+
+__device__ __forceinline__ void warp_exchange8(const double (&sr)[8], const double (&si)[8], double (&rr)[8], double (&ri)[8])
+{
+#pragma unroll
+    for (int s = 0; s < 8; s++) { rr[s] = __shfl_xor_sync(0xffffffffu, sr[s], 16); ri[s] = __shfl_xor_sync(0xffffffffu, si[s], 16); }
+}
+
+template <int L>
+__global__ void __launch_bounds__(128, 2)
+blind_rotate_warp_kernel(DevParams p, const double2 *__restrict__ bkw, GateAddr ga, const int32_t *__restrict__ baseA,
+                         const int32_t *__restrict__ baseB, int32_t *__restrict__ ext)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t tmem_base_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, lpar = lane >> 4;
+    unsigned char *base = smem_raw + (size_t)warp * kWarpGateSmem;
+    int32_t *acc = reinterpret_cast<int32_t *>(base);
+    cd *buf = reinterpret_cast<cd *>(base + kAccBytes);
+    uint16_t *abar = reinterpret_cast<uint16_t *>(base + kAccBytes + kWarpBufElems * 16);
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(&tmem_base_slot)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    const int n = p.n;
+    const long long total = (long long)ga.ntempl * ga.n_inst;
+    long long g = (long long)blockIdx.x * 4 + warp;
+    const bool active = g < total;
+    if (!active) g = total - 1; /* idle warps shadow the last gate and write nothing: the CTA frees its TMEM together */
+    {
+        const int e = (int)(g / ga.ntempl), t = (int)(g - (long long)e * ga.ntempl);
+        GateT gt = ga.uni;
+        if (ga.tmpl) gt = ga.tmpl[t]; else { gt.in0 = (gt.in0 >= 0) ? t : -1; gt.in1 = (gt.in1 >= 0) ? t : -1; }
+        const size_t blk = (size_t)e * ga.inst_samples;
+        const int32_t *in0 = gt.in0 >= 0 ? baseA + (blk + gt.in0) * ga.stride : nullptr;
+        const int32_t *in1 = gt.in1 >= 0 ? baseB + (blk + gt.in1) * ga.stride : nullptr;
+        const int32_t c0 = gt.c0, c1 = gt.c1, cst = gt.cst_mu * p.mu;
+        for (int i = lane; i <= n; i += 32) {
+            int32_t v = (i == n) ? cst : 0;
+            if (in0) v += c0 * __ldg(in0 + i);
+            if (in1) v += c1 * __ldg(in1 + i);
+            abar[i] = (uint16_t)modswitch_2N(v);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t taddr = tmem_base_slot + ((uint32_t)(warp * 32) << 16);
+    {
+        const int bbar = abar[n];
+        const int a = (2 * kN - bbar) & (2 * kN - 1), ar = a & (kN - 1);
+        const bool flip = a >= kN;
+        for (int j = lane; j < kN; j += 32) { acc[j] = 0; acc[kN + j] = ((j < ar) != flip) ? -p.mu : p.mu; }
+    }
+    __syncwarp();
+
+    const Tw16 w1 = tw16_pass1();
+    const Tw16 w2 = d_tw16[lane & 15];
+    const FinTw fin = d_fin[lane];
+    const int Bgbit = p.Bgbit;
+    const uint32_t maskBg = (1u << Bgbit) - 1;
+    const int32_t halfBg = 1 << (Bgbit - 1);
+    uint32_t offset = 0;
+#pragma unroll
+    for (int i = 1; i <= L; i++) offset += (uint32_t)halfBg << (32 - i * Bgbit);
+    constexpr int kRowElems = 2 * kHalfN, kBkStride = 2 * L * kRowElems;
+
+    for (int i = 0; i < n; i++) {
+        const int a = abar[i];
+        const double2 *bk_r = bkw + (size_t)i * kBkStride + lane;
+        bool first = true;
+#pragma unroll 1
+        for (int q = 0; q < 2; q++) {
+            int32_t c[32];
+            rot_minus_one32(acc + q * kN, lane, a, c);
+#pragma unroll 1
+            for (int pp = 0; pp < L; pp++) {
+                const int shift = 32 - (pp + 1) * Bgbit;
+                double xr[16], xi[16];
+#pragma unroll
+                for (int m = 0; m < 16; m++) {
+                    xr[m] = digit_f64_magic(c[m], offset, shift, maskBg, halfBg);
+                    xi[m] = digit_f64_magic(c[16 + m], offset, shift, maskBg, halfBg);
+                }
+                /* forward transform */
+                pass16_fwd(xr, xi, w1);
+                __syncwarp();                      /* every lane has finished reading the buffer of the previous transform */
+                st16_pass1(buf, lane, xr, xi);
+                __syncwarp();
+                ld16_pass2(buf, lane, xr, xi);
+                pass16_fwd(xr, xi, w2);
+                {
+                    double sr[8], si[8], rr[8], ri[8];
+                    fin_fwd_send(xr, xi, lpar, sr, si);
+                    warp_exchange8(sr, si, rr, ri);
+                    fin_fwd_apply(xr, xi, lpar, rr, ri, fin.zr, fin.zi);
+                }
+                /* multiply-accumulate into TMEM: 8 slots of one output polynomial at a time.  (Eight pipelined chunks of 4
+                 * slots - accumulators and BK_i of chunk c+1 requested before chunk c is computed - were measured much
+                 * slower, 72 k against 99 k gates/s: twice the tcgen05 round trips, and spills.) */
+                if (!first) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        double sacc[16];
+                        double2 bj[8];
+#pragma unroll
+                        for (int r = 0; r < 8; r++) bj[r] = __ldg(bk_r + (j * 16 + 8 * h + r) * 32);
+                        const uint32_t tj = taddr + (uint32_t)((j * 16 + 8 * h) * 4);
+                        if (!first) {
+                            IE_TMEM_LD16D(tj, sacc);
+                        } else {
+#pragma unroll
+                            for (int r = 0; r < 16; r++) sacc[r] = 0.0;
+                        }
+#pragma unroll
+                        for (int r = 0; r < 8; r++) cmac(sacc[2 * r], sacc[2 * r + 1], xr[8 * h + r], xi[8 * h + r], bj[r].x, bj[r].y);
+                        IE_TMEM_ST16D(tj, sacc);
+                    }
+                }
+                first = false;
+                bk_r += kRowElems;
+            }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        /* inverse transforms and ACC update */
+#pragma unroll 1
+        for (int j = 0; j < 2; j++) {
+            double xr[16], xi[16];
+            {
+                double s0[16], s1[16];
+                IE_TMEM_LD16D(taddr + (uint32_t)(j * 64), s0);
+                IE_TMEM_LD16D(taddr + (uint32_t)(j * 64 + 32), s1);
+#pragma unroll
+                for (int r = 0; r < 8; r++) { xr[r] = s0[2 * r]; xi[r] = s0[2 * r + 1]; xr[8 + r] = s1[2 * r]; xi[8 + r] = s1[2 * r + 1]; }
+            }
+            fin_inv_local(xr, xi, fin.zr, fin.zi);
+            {
+                double sr[8], si[8], rr[8], ri[8];
+                fin_inv_send(xr, xi, lpar, sr, si);
+                warp_exchange8(sr, si, rr, ri);
+                fin_inv_place(xr, xi, lpar, rr, ri);
+            }
+            pass16_inv(xr, xi, w2);
+            __syncwarp();
+            st16_ipass2(buf, lane, xr, xi);
+            __syncwarp();
+            ld16_ipass1(buf, lane, xr, xi);
+            pass16_inv(xr, xi, w1);
+            int32_t *accj = acc + j * kN;
+#pragma unroll
+            for (int m = 0; m < 16; m++) {
+                accj[lane + 32 * m] += round_to_torus(xr[m]);
+                accj[lane + 32 * m + 512] += round_to_torus(xi[m]);
+            }
+        }
+        __syncwarp();
+    }
+
+    if (active) {
+        int32_t *o = ext + (size_t)g * kExtStride;
+        for (int j = lane; j < kN; j += 32) o[j] = (j == 0) ? acc[0] : -acc[kN - j];
+        if (lane == 0) o[kN] = acc[kN];
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem_base_slot));
+}
+
+template <int L>
+static cudaError_t launch_br_warp(const DevParams &p, const double2 *bkw, const GateAddr &ga, const int32_t *baseA,
+                                  const int32_t *baseB, int32_t *ext, long long count, cudaStream_t s)
+{
+    constexpr int smem = 4 * kWarpGateSmem;
+    cudaError_t e = cudaFuncSetAttribute(blind_rotate_warp_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    blind_rotate_warp_kernel<L><<<(int)((count + 3) / 4), 128, smem, s>>>(p, bkw, ga, baseA, baseB, ext);
+    return cudaGetLastError();
+}
+
 /* ---- latency variant with two groups per gate: group q owns ACC polynomial q, runs its l forward transforms
  * with register accumulators for both output polynomials, hands the partial sum of the *other* polynomial to
  * the other group through 8 KB of shared memory, and inverts / updates its own polynomial.  Per step: 4
@@ -865,12 +1076,13 @@ void set_cluster_max(long long v) { g_cluster_max = v; }
 long long get_cluster_max() { return g_cluster_max; }
 
 /* launch configuration: IEACHE_BR_VARIANT selects among the compiled variants (tuning aid) */
+static int g_br_variant = -1;
 static int br_variant()
 {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("IEACHE_BR_VARIANT"); v = e ? atoi(e) : 41; }
-    return v;
+    if (g_br_variant < 0) { const char *e = getenv("IEACHE_BR_VARIANT"); g_br_variant = e ? atoi(e) : 41; }
+    return g_br_variant;
 }
+int set_throughput_variant(int v) { const int old = br_variant(); if (v >= 0) g_br_variant = v; return old; }
 int blind_rotate_groups_per_cta() { const int v = br_variant(); return (v == 4 || v == 11 || v == 13 || v == 31 || v == 34) ? 4 : ((v == 0 || v == 1 || v == 3 || v == 5 || v == 6 || v == 12 || v == 30 || v == 32 || v == 33) ? 2 : 1); }
 int blind_rotate_smem_bytes(int groups) { return groups * kGroupSmem; }
 
@@ -886,7 +1098,12 @@ static cudaError_t launch_br_variant(const DevParams &p, const double2 *bkfft, c
     return cudaGetLastError();
 }
 
-cudaError_t launch_blind_rotate(const DevParams &p, const double2 *bkfft, const GateAddr &ga, const int32_t *baseA,
+bool blind_rotate_uses_warp_layout(long long count)
+{
+    return br_variant() == 60 && count > 0;
+}
+
+cudaError_t launch_blind_rotate(const DevParams &p, const double2 *bkfft, const double2 *bkfft_w, const GateAddr &ga, const int32_t *baseA,
                                 const int32_t *baseB, int32_t *ext, int ext_base, cudaStream_t s)
 {
     const long long count = (long long)ga.ntempl * ga.n_inst;
@@ -910,6 +1127,10 @@ cudaError_t launch_blind_rotate(const DevParams &p, const double2 *bkfft, const 
     if (two_group) {
         if (p.l == 3) return launch_br_pair<3>(p, bkfft, ga, baseA, baseB, ext, count, s);
         if (p.l == 2) return launch_br_pair<2>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    }
+    if (bkfft_w && br_variant() == 60) {
+        if (p.l == 3) return launch_br_warp<3>(p, bkfft_w, ga, baseA, baseB, ext, count, s);
+        if (p.l == 2) return launch_br_warp<2>(p, bkfft_w, ga, baseA, baseB, ext, count, s);
     }
     if (p.l == 2) return launch_br_variant<2, 1, 4, 2>(p, bkfft, ga, baseA, baseB, ext, count, s);
     if (p.l != 3) return cudaErrorInvalidValue;

@@ -75,6 +75,11 @@ int64_t ieache_set_wide_max(int64_t max_gates);
  * pair of SMs (thread-block cluster of 2, products exchanged through distributed shared memory).  Same calling
  * convention as ieache_set_wide_max.  Default 74 (148 SMs / 2: one wave). */
 int64_t ieache_set_cluster_max(int64_t max_gates);
+/* Which compiled variant of the throughput blind rotation wide launches use: 41 (default) keeps the accumulators in
+ * registers, one 64-thread group per gate; 60 is the warp-per-gate kernel (16 points per lane, accumulators in tensor
+ * memory); 51/52/55/56 keep 64-thread groups with TMEM accumulators.  All give the same results (same parity tests);
+ * a negative argument only queries.  Returns the previous value.  Tuning / test aid. */
+int ieache_set_throughput_variant(int variant);
 /* Key-switch launches of at least min_gates gates use the staged kernel (the key rows of one input position are
  * copied to shared memory once per 12 gates); smaller ones gather rows per gate.  Same calling convention.
  * Default 1000 (where the two kernels cross).  Both kernels give bit-identical results. */

@@ -9,6 +9,7 @@
  * GPU run is spent.  It is NOT part of the product library and is never a fallback.
  */
 #include "../../ie-ache_b200/csrc/br_core.h"
+#include "../../ie-ache_b200/csrc/br_warp.h"
 
 #include <cstdlib>
 #include <cstring>
@@ -131,6 +132,136 @@ void emul_blind_rotate(int n, int l, int Bgbit, int32_t mu, const int32_t *bk_co
                 for (int m = 0; m < 8; m++) {
                     acc[j * kN + tid + 64 * m] += round_to_torus(t[tid].xr[m]);
                     acc[j * kN + tid + 64 * m + 512] += round_to_torus(t[tid].xi[m]);
+                }
+        }
+    }
+    for (int j = 0; j < kN; j++) ext[j] = (j == 0) ? acc[0] : -acc[kN - j];
+    ext[kN] = acc[kN];
+}
+
+} // extern "C"
+
+/* ------------------------------------------------------------------ warp-per-gate layout (br_warp.h) */
+namespace {
+struct Regs16 { double xr[16], xi[16]; };
+struct EmulW {
+    Tw16 w1, w2[16];
+    FinTw fin[32];
+    EmulW() { w1 = tw16_pass1(); host_twiddles_warp(w2, fin); }
+    void fwd(Regs16 *t, cd *buf) const
+    {
+        for (int l = 0; l < 32; l++) { pass16_fwd(t[l].xr, t[l].xi, w1); st16_pass1(buf, l, t[l].xr, t[l].xi); }
+        for (int l = 0; l < 32; l++) { ld16_pass2(buf, l, t[l].xr, t[l].xi); pass16_fwd(t[l].xr, t[l].xi, w2[l & 15]); }
+        double sr[32][8], si[32][8];
+        for (int l = 0; l < 32; l++) fin_fwd_send(t[l].xr, t[l].xi, l >> 4, sr[l], si[l]);
+        for (int l = 0; l < 32; l++) fin_fwd_apply(t[l].xr, t[l].xi, l >> 4, sr[l ^ 16], si[l ^ 16], fin[l].zr, fin[l].zi); /* shfl_xor 16 */
+    }
+    void inv(Regs16 *t, cd *buf) const
+    {
+        double sr[32][8], si[32][8];
+        for (int l = 0; l < 32; l++) { fin_inv_local(t[l].xr, t[l].xi, fin[l].zr, fin[l].zi); fin_inv_send(t[l].xr, t[l].xi, l >> 4, sr[l], si[l]); }
+        for (int l = 0; l < 32; l++) fin_inv_place(t[l].xr, t[l].xi, l >> 4, sr[l ^ 16], si[l ^ 16]);
+        for (int l = 0; l < 32; l++) { pass16_inv(t[l].xr, t[l].xi, w2[l & 15]); st16_ipass2(buf, l, t[l].xr, t[l].xi); }
+        for (int l = 0; l < 32; l++) { ld16_ipass1(buf, l, t[l].xr, t[l].xi); pass16_inv(t[l].xr, t[l].xi, w1); }
+    }
+};
+const EmulW &emulw() { static EmulW e; return e; }
+} // namespace
+
+extern "C" {
+
+/* forward transform into the warp layout [p][lane] (re,im) */
+void emul_warp_fft(const int32_t *coef, double *out /*512*2*/, double scale)
+{
+    const EmulW &e = emulw();
+    Regs16 t[32];
+    cd buf[kWarpBufElems];
+    for (int l = 0; l < 32; l++)
+        for (int m = 0; m < 16; m++) { t[l].xr[m] = (double)coef[l + 32 * m]; t[l].xi[m] = (double)coef[l + 32 * m + 512]; }
+    e.fwd(t, buf);
+    for (int l = 0; l < 32; l++)
+        for (int p = 0; p < 16; p++) { out[2 * (p * 32 + l)] = t[l].xr[p] * scale; out[2 * (p * 32 + l) + 1] = t[l].xi[p] * scale; }
+}
+void emul_warp_ifft(const double *in /*512*2*/, double *coef_out /*1024*/)
+{
+    const EmulW &e = emulw();
+    Regs16 t[32];
+    cd buf[kWarpBufElems];
+    for (int l = 0; l < 32; l++)
+        for (int p = 0; p < 16; p++) { t[l].xr[p] = in[2 * (p * 32 + l)]; t[l].xi[p] = in[2 * (p * 32 + l) + 1]; }
+    e.inv(t, buf);
+    for (int l = 0; l < 32; l++)
+        for (int m = 0; m < 16; m++) { coef_out[l + 32 * m] = t[l].xr[m]; coef_out[l + 32 * m + 512] = t[l].xi[m]; }
+}
+int emul_warp_slot_to_K(int p, int lane) { return warp_slot_to_K(p, lane); }
+
+/* whole blind rotation + sample extract with the warp layout (BK relaid out through emul_slot_to_K / warp_slot_to_K,
+ * exactly what the key-load kernel does on the device) */
+void emul_warp_blind_rotate(int n, int l, int Bgbit, int32_t mu, const int32_t *bk_coef, const int32_t *x, int32_t *ext)
+{
+    const EmulW &e = emulw();
+    const int kpl = 2 * l;
+    std::vector<double> bkw((size_t)n * kpl * 2 * 1024);
+    {
+        /* old layout first, then the permutation old [r8][t64] -> new [p16][lane32] */
+        int pos_of_K[512];
+        for (int r = 0; r < 8; r++) for (int t3 = 0; t3 < 64; t3++) pos_of_K[emul_slot_to_K(r, t3)] = r * 64 + t3;
+        std::vector<double> old(1024);
+        for (long q = 0; q < (long)n * kpl * 2; q++) {
+            emul_poly_fft(bk_coef + (size_t)q * kN, old.data(), 1.0 / 512.0);
+            double *dst = &bkw[(size_t)q * 1024];
+            for (int p = 0; p < 16; p++) for (int lane = 0; lane < 32; lane++) {
+                const int src = pos_of_K[warp_slot_to_K(p, lane)];
+                dst[2 * (p * 32 + lane)] = old[2 * src]; dst[2 * (p * 32 + lane) + 1] = old[2 * src + 1];
+            }
+        }
+    }
+    std::vector<int32_t> acc(2 * kN);
+    std::vector<int> abar(n + 1);
+    for (int i = 0; i <= n; i++) abar[i] = modswitch_2N(x[i]);
+    {
+        const int a = (2 * kN - abar[n]) & (2 * kN - 1), ar = a & (kN - 1);
+        const bool flip = a >= kN;
+        for (int j = 0; j < kN; j++) { acc[j] = 0; acc[kN + j] = ((j < ar) != flip) ? -mu : mu; }
+    }
+    const uint32_t maskBg = (1u << Bgbit) - 1;
+    const int32_t halfBg = 1 << (Bgbit - 1);
+    uint32_t offset = 0;
+    for (int i = 1; i <= l; i++) offset += (uint32_t)halfBg << (32 - i * Bgbit);
+    Regs16 t[32];
+    cd buf[kWarpBufElems];
+    std::vector<double> sr(32 * 2 * 16), si(32 * 2 * 16);
+    for (int i = 0; i < n; i++) {
+        const int a = abar[i];
+        std::fill(sr.begin(), sr.end(), 0.0); std::fill(si.begin(), si.end(), 0.0);
+        for (int q = 0; q < 2; q++) {
+            int32_t c[32][32];
+            for (int lane = 0; lane < 32; lane++) rot_minus_one32(&acc[q * kN], lane, a, c[lane]);
+            for (int pp = 0; pp < l; pp++) {
+                const int shift = 32 - (pp + 1) * Bgbit;
+                for (int lane = 0; lane < 32; lane++)
+                    for (int m = 0; m < 16; m++) {
+                        t[lane].xr[m] = digit_f64(c[lane][m], offset, shift, maskBg, halfBg);
+                        t[lane].xi[m] = digit_f64(c[lane][16 + m], offset, shift, maskBg, halfBg);
+                    }
+                e.fwd(t, buf);
+                const double *bk_r = &bkw[(((size_t)i * kpl + q * l + pp) * 2) * 1024];
+                for (int lane = 0; lane < 32; lane++)
+                    for (int j = 0; j < 2; j++)
+                        for (int p = 0; p < 16; p++) {
+                            const double *b = bk_r + (size_t)j * 1024 + 2 * (p * 32 + lane);
+                            cmac(sr[(lane * 2 + j) * 16 + p], si[(lane * 2 + j) * 16 + p], t[lane].xr[p], t[lane].xi[p], b[0], b[1]);
+                        }
+            }
+        }
+        for (int j = 0; j < 2; j++) {
+            for (int lane = 0; lane < 32; lane++)
+                for (int p = 0; p < 16; p++) { t[lane].xr[p] = sr[(lane * 2 + j) * 16 + p]; t[lane].xi[p] = si[(lane * 2 + j) * 16 + p]; }
+            e.inv(t, buf);
+            for (int lane = 0; lane < 32; lane++)
+                for (int m = 0; m < 16; m++) {
+                    acc[j * kN + lane + 32 * m] += round_to_torus(t[lane].xr[m]);
+                    acc[j * kN + lane + 32 * m + 512] += round_to_torus(t[lane].xi[m]);
                 }
         }
     }

@@ -83,3 +83,61 @@ def test_blind_rotate_matches_oracle(emul, oracle, n, l, bgbit):
         d = ((d + 2 ** 31) % 2 ** 32) - 2 ** 31
         assert np.abs(d).max() <= 2   # FP64 rounding may differ in the last unit; normally 0
     ks.free()
+
+
+# ---- warp-per-gate layout (ie-ache_b200/csrc/br_warp.h): 16 points per lane, one exchange + one shuffle stage
+
+def test_warp_slot_order_is_evaluation_at_odd_roots(emul):
+    emul.emul_warp_slot_to_K.restype = ctypes.c_int
+    rng = np.random.default_rng(13)
+    a = rng.integers(-64, 64, 1024).astype(np.int32)
+    fa = np.zeros(1024)
+    emul.emul_warp_fft(vp(a), vp(fa), ctypes.c_double(1.0))
+    ca = fa[0::2] + 1j * fa[1::2]
+    psi = np.exp(1j * np.pi / 1024)
+    for p in range(16):
+        for lane in (0, 5, 15, 16, 22, 31):
+            K = emul.emul_warp_slot_to_K(p, lane)
+            val = np.polyval(a[::-1].astype(np.complex128), psi ** (4 * K + 1))
+            assert abs(val - ca[p * 32 + lane]) < 1e-6, (p, lane, K)
+    assert sorted(emul.emul_warp_slot_to_K(p, l) for p in range(16) for l in range(32)) == list(range(512))
+
+
+def test_warp_negacyclic_product_is_exact(emul):
+    rng = np.random.default_rng(14)
+    a = rng.integers(-64, 64, 1024).astype(np.int32)
+    b = rng.integers(-2 ** 31, 2 ** 31, 1024).astype(np.int32)
+    fa, fb = np.zeros(1024), np.zeros(1024)
+    emul.emul_warp_fft(vp(a), vp(fa), ctypes.c_double(1.0))
+    emul.emul_warp_fft(vp(b), vp(fb), ctypes.c_double(1.0 / 512))
+    prod = (fa[0::2] + 1j * fa[1::2]) * (fb[0::2] + 1j * fb[1::2])
+    pin = np.zeros(1024)
+    pin[0::2], pin[1::2] = prod.real, prod.imag
+    out = np.zeros(1024)
+    emul.emul_warp_ifft(vp(pin), vp(out))
+    full = np.convolve(a.astype(object), b.astype(object))
+    ref = [int(full[i]) - (int(full[i + 1024]) if i + 1024 < len(full) else 0) for i in range(1024)]
+    assert max(abs(out[i] - ref[i]) for i in range(1024)) < 0.25
+
+
+@pytest.mark.parametrize("n,l,bgbit", [(24, 3, 7), (12, 2, 10)])
+def test_warp_blind_rotate_matches_oracle(emul, oracle, n, l, bgbit):
+    p = ob.params_default(n)
+    p.bk_l, p.bk_Bgbit = l, bgbit
+    ks = oracle.keygen(p, seed=778)
+    bits = np.array([1, 0, 1, 1, 0, 0], dtype=np.int32)
+    s = ks.encrypt(bits, 6)
+    mu = 1 << 29
+    bk = ks.bk_coef()
+    for g in range(6):
+        x = (s[g] + s[(g + 1) % 6]).astype(np.int32)
+        x[n] -= mu
+        ext_o = ks.bootstrap_woks(x[None])[0]
+        ext_e = np.zeros(1025, dtype=np.int32)
+        emul.emul_warp_blind_rotate(n, l, bgbit, ctypes.c_int32(mu), vp(bk), vp(x), vp(ext_e))
+        ph = ks.phase_extracted(ext_e[None])[0]
+        assert (ph > 0) == bool(bits[g] & bits[(g + 1) % 6])
+        d = ext_o.astype(np.int64) - ext_e.astype(np.int64)
+        d = ((d + 2 ** 31) % 2 ** 32) - 2 ** 31
+        assert np.abs(d).max() <= 2
+    ks.free()
