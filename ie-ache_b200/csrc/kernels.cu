@@ -541,7 +541,12 @@ blind_rotate_warp_kernel(DevParams p, const double2 *__restrict__ bkw, GateAddr 
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t tmem_base_slot;
+    __shared__ double s_finr[8][32], s_fini[8][32]; /* final-stage twiddles [s][lane]: 32 registers per thread otherwise */
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, lpar = lane >> 4;
+    if (warp == 1) {
+#pragma unroll
+        for (int s8 = 0; s8 < 8; s8++) { s_finr[s8][lane] = d_fin[lane].zr[s8]; s_fini[s8][lane] = d_fin[lane].zi[s8]; }
+    }
     unsigned char *base = smem_raw + (size_t)warp * kWarpGateSmem;
     int32_t *acc = reinterpret_cast<int32_t *>(base);
     cd *buf = reinterpret_cast<cd *>(base + kAccBytes);
@@ -585,7 +590,6 @@ blind_rotate_warp_kernel(DevParams p, const double2 *__restrict__ bkw, GateAddr 
 
     const Tw16 w1 = tw16_pass1();
     const Tw16 w2 = d_tw16[lane & 15];
-    const FinTw fin = d_fin[lane];
     const int Bgbit = p.Bgbit;
     const uint32_t maskBg = (1u << Bgbit) - 1;
     const int32_t halfBg = 1 << (Bgbit - 1);
@@ -619,34 +623,42 @@ blind_rotate_warp_kernel(DevParams p, const double2 *__restrict__ bkw, GateAddr 
                 ld16_pass2(buf, lane, xr, xi);
                 pass16_fwd(xr, xi, w2);
                 {
-                    double sr[8], si[8], rr[8], ri[8];
+                    double sr[8], si[8], rr[8], ri[8], fzr[8], fzi[8];
                     fin_fwd_send(xr, xi, lpar, sr, si);
                     warp_exchange8(sr, si, rr, ri);
-                    fin_fwd_apply(xr, xi, lpar, rr, ri, fin.zr, fin.zi);
+#pragma unroll
+                    for (int s8 = 0; s8 < 8; s8++) { fzr[s8] = s_finr[s8][lane]; fzi[s8] = s_fini[s8][lane]; }
+                    fin_fwd_apply(xr, xi, lpar, rr, ri, fzr, fzi);
                 }
-                /* multiply-accumulate into TMEM: 8 slots of one output polynomial at a time.  (Eight pipelined chunks of 4
-                 * slots - accumulators and BK_i of chunk c+1 requested before chunk c is computed - were measured much
-                 * slower, 72 k against 99 k gates/s: twice the tcgen05 round trips, and spills.) */
+                /* multiply-accumulate into TMEM: 8 slots of one output polynomial at a time; the BK_i values of chunk
+                 * c+1 are requested before chunk c is computed (the registers come from keeping the final-stage
+                 * twiddles in shared memory: 98.9 k -> 107.8 k gates/s).  Measured and rejected: 8 pipelined chunks of 4
+                 * slots (72 k: twice the tcgen05 round trips, spills); zeroing the accumulators with stores at the
+                 * start of a step instead of the `first` special case (89 k: 116 bytes of spills - the kernel sits at
+                 * 254 registers). */
                 if (!first) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                double2 bj[2][8];
 #pragma unroll
-                for (int j = 0; j < 2; j++) {
+                for (int r = 0; r < 8; r++) bj[0][r] = __ldg(bk_r + r * 32);
 #pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        double sacc[16];
-                        double2 bj[8];
+                for (int cidx = 0; cidx < 4; cidx++) {
+                    const int cur = cidx & 1, nxt = cur ^ 1;
+                    if (cidx + 1 < 4) {
 #pragma unroll
-                        for (int r = 0; r < 8; r++) bj[r] = __ldg(bk_r + (j * 16 + 8 * h + r) * 32);
-                        const uint32_t tj = taddr + (uint32_t)((j * 16 + 8 * h) * 4);
-                        if (!first) {
-                            IE_TMEM_LD16D(tj, sacc);
-                        } else {
-#pragma unroll
-                            for (int r = 0; r < 16; r++) sacc[r] = 0.0;
-                        }
-#pragma unroll
-                        for (int r = 0; r < 8; r++) cmac(sacc[2 * r], sacc[2 * r + 1], xr[8 * h + r], xi[8 * h + r], bj[r].x, bj[r].y);
-                        IE_TMEM_ST16D(tj, sacc);
+                        for (int r = 0; r < 8; r++) bj[nxt][r] = __ldg(bk_r + (8 * (cidx + 1) + r) * 32);
                     }
+                    double sacc[16];
+                    const uint32_t tj = taddr + (uint32_t)(32 * cidx);
+                    if (!first) {
+                        IE_TMEM_LD16D(tj, sacc);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 16; r++) sacc[r] = 0.0;
+                    }
+                    const int sl = 8 * (cidx & 1); /* slots 8h..8h+7 of polynomial cidx >> 1 */
+#pragma unroll
+                    for (int r = 0; r < 8; r++) cmac(sacc[2 * r], sacc[2 * r + 1], xr[sl + r], xi[sl + r], bj[cur][r].x, bj[cur][r].y);
+                    IE_TMEM_ST16D(tj, sacc);
                 }
                 first = false;
                 bk_r += kRowElems;
@@ -664,7 +676,12 @@ blind_rotate_warp_kernel(DevParams p, const double2 *__restrict__ bkw, GateAddr 
 #pragma unroll
                 for (int r = 0; r < 8; r++) { xr[r] = s0[2 * r]; xi[r] = s0[2 * r + 1]; xr[8 + r] = s1[2 * r]; xi[8 + r] = s1[2 * r + 1]; }
             }
-            fin_inv_local(xr, xi, fin.zr, fin.zi);
+            {
+                double fzr[8], fzi[8];
+#pragma unroll
+                for (int s8 = 0; s8 < 8; s8++) { fzr[s8] = s_finr[s8][lane]; fzi[s8] = s_fini[s8][lane]; }
+                fin_inv_local(xr, xi, fzr, fzi);
+            }
             {
                 double sr[8], si[8], rr[8], ri[8];
                 fin_inv_send(xr, xi, lpar, sr, si);
