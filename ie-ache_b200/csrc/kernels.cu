@@ -542,16 +542,10 @@ blind_rotate_warp_kernel(DevParams p, const double2 *__restrict__ bkw, GateAddr 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t tmem_base_slot;
     __shared__ double s_finr[8][32], s_fini[8][32]; /* final-stage twiddles [s][lane]: 32 registers per thread otherwise */
-    __shared__ double s_tw2[16][16];                /* pass-2 twiddles [value][k]: another 32 registers */
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, lpar = lane >> 4;
     if (warp == 1) {
 #pragma unroll
         for (int s8 = 0; s8 < 8; s8++) { s_finr[s8][lane] = d_fin[lane].zr[s8]; s_fini[s8][lane] = d_fin[lane].zi[s8]; }
-    }
-    if (warp == 2 && lane < 16) {
-        const double *src = reinterpret_cast<const double *>(&d_tw16[lane]);
-#pragma unroll
-        for (int v = 0; v < 16; v++) s_tw2[v][lane] = src[v];
     }
     unsigned char *base = smem_raw + (size_t)warp * kWarpGateSmem;
     int32_t *acc = reinterpret_cast<int32_t *>(base);
@@ -595,13 +589,7 @@ blind_rotate_warp_kernel(DevParams p, const double2 *__restrict__ bkw, GateAddr 
     __syncwarp();
 
     const Tw16 w1 = tw16_pass1();
-    auto load_w2 = [&]() {
-        Tw16 w;
-        double *dst = reinterpret_cast<double *>(&w);
-#pragma unroll
-        for (int v = 0; v < 16; v++) dst[v] = s_tw2[v][lane & 15];
-        return w;
-    };
+    const Tw16 w2 = d_tw16[lane & 15];
     const int Bgbit = p.Bgbit;
     const uint32_t maskBg = (1u << Bgbit) - 1;
     const int32_t halfBg = 1 << (Bgbit - 1);
@@ -633,7 +621,7 @@ blind_rotate_warp_kernel(DevParams p, const double2 *__restrict__ bkw, GateAddr 
                 st16_pass1(buf, lane, xr, xi);
                 __syncwarp();
                 ld16_pass2(buf, lane, xr, xi);
-                { const Tw16 w2 = load_w2(); pass16_fwd(xr, xi, w2); }
+                pass16_fwd(xr, xi, w2);
                 {
                     double sr[8], si[8], rr[8], ri[8], fzr[8], fzi[8];
                     fin_fwd_send(xr, xi, lpar, sr, si);
@@ -700,7 +688,7 @@ blind_rotate_warp_kernel(DevParams p, const double2 *__restrict__ bkw, GateAddr 
                 warp_exchange8(sr, si, rr, ri);
                 fin_inv_place(xr, xi, lpar, rr, ri);
             }
-            { const Tw16 w2 = load_w2(); pass16_inv(xr, xi, w2); }
+            pass16_inv(xr, xi, w2);
             __syncwarp();
             st16_ipass2(buf, lane, xr, xi);
             __syncwarp();
