@@ -637,16 +637,11 @@ blind_rotate_warp_kernel(DevParams p, const double2 *__restrict__ bkw, GateAddr 
                  * start of a step instead of the `first` special case (89 k: 116 bytes of spills - the kernel sits at
                  * 254 registers). */
                 if (!first) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                double2 bj[2][8];
+                double2 bj[8];
 #pragma unroll
-                for (int r = 0; r < 8; r++) bj[0][r] = __ldg(bk_r + r * 32);
+                for (int r = 0; r < 8; r++) bj[r] = __ldg(bk_r + r * 32);
 #pragma unroll
                 for (int cidx = 0; cidx < 4; cidx++) {
-                    const int cur = cidx & 1, nxt = cur ^ 1;
-                    if (cidx + 1 < 4) {
-#pragma unroll
-                        for (int r = 0; r < 8; r++) bj[nxt][r] = __ldg(bk_r + (8 * (cidx + 1) + r) * 32);
-                    }
                     double sacc[16];
                     const uint32_t tj = taddr + (uint32_t)(32 * cidx);
                     if (!first) {
@@ -657,7 +652,11 @@ blind_rotate_warp_kernel(DevParams p, const double2 *__restrict__ bkw, GateAddr 
                     }
                     const int sl = 8 * (cidx & 1); /* slots 8h..8h+7 of polynomial cidx >> 1 */
 #pragma unroll
-                    for (int r = 0; r < 8; r++) cmac(sacc[2 * r], sacc[2 * r + 1], xr[sl + r], xi[sl + r], bj[cur][r].x, bj[cur][r].y);
+                    for (int r = 0; r < 8; r++) cmac(sacc[2 * r], sacc[2 * r + 1], xr[sl + r], xi[sl + r], bj[r].x, bj[r].y);
+                    if (cidx + 1 < 4) { /* the next chunk's BK_i values go into the registers just consumed, under the TMEM round trip */
+#pragma unroll
+                        for (int r = 0; r < 8; r++) bj[r] = ldg_pinned(bk_r + (8 * (cidx + 1) + r) * 32);
+                    }
                     IE_TMEM_ST16D(tj, sacc);
                 }
                 first = false;
