@@ -113,7 +113,7 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return 0
-    per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    per_step = args.ref_seconds or max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
     rates = []
     for i in range(args.warmup + args.steps):
         r, threads, done, dt = cpu_port_rate(per_step)
@@ -217,6 +217,7 @@ def main():
                     help="nand: BASELINE.json config 2 (the metric's configuration, default); muladd / mul64: a time-boxed subset of "
                          "configs 4 / 5 (independent a*b+c expressions / 64-bit multiplies, --n-expr per GPU) through the levelised circuits")
     ap.add_argument("--n-expr", type=int, default=64, help="expressions per GPU and step for --workload muladd / mul64")
+    ap.add_argument("--ref-seconds", type=float, default=0.0, help="--impl reference: seconds of CPU work per step (default: sized so the run ends within ~2 minutes)")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-expression", action="store_true")
     args = ap.parse_args()
