@@ -160,6 +160,52 @@ IE_HD void fin_inv_place(double (&xr)[16], double (&xi)[16], int lpar, const dou
     }
 }
 
+/* ---- "folded" forward variant: no lane-dependent selects in the final stage ----
+ * The Lpar = 1 lane runs pass 2 with the twiddles of its two 8-point blocks exchanged (and -z8), which leaves its 16
+ * results with the register halves swapped: register s holds root s + 8, register 8 + s holds root s.  Both lanes of a
+ * pair then send registers 8..15 and keep 0..7, and both compute keep +- w * received:
+ *   Lpar = 0: keep = R_0[s],   recv = R_1[s],   w = Y           -> out_+ , out_-           (as before)
+ *   Lpar = 1: keep = R_1[8+s], recv = R_0[8+s], w = conj(Y)     -> out_+ / Y , -out_- / Y
+ * The unit-modulus factors of the Lpar = 1 lane are multiplied into the bootstrapping key when it is laid out
+ * (folded_bk_factor), so the products that reach the accumulators are the true ones and the inverse is unchanged. */
+struct Tw16g { double z8r, z8i, z4ar, z4ai, z4br, z4bi, z2ar, z2ai, z2br, z2bi, z1ar, z1ai, z1aqr, z1aqi, z1br, z1bi, z1bqr, z1bqi; };
+
+IE_HD void pass16_fwd_g(double (&xr)[16], double (&xi)[16], const Tw16g &w)
+{
+#pragma unroll
+    for (int m = 0; m < 8; m++) bf(xr[m], xi[m], xr[m + 8], xi[m + 8], w.z8r, w.z8i);
+#pragma unroll
+    for (int m = 0; m < 4; m++) bf(xr[m], xi[m], xr[m + 4], xi[m + 4], w.z4ar, w.z4ai);
+#pragma unroll
+    for (int m = 8; m < 12; m++) bf(xr[m], xi[m], xr[m + 4], xi[m + 4], w.z4br, w.z4bi);
+#pragma unroll
+    for (int m = 0; m < 2; m++) {
+        bf(xr[m], xi[m], xr[m + 2], xi[m + 2], w.z2ar, w.z2ai);
+        bf(xr[4 + m], xi[4 + m], xr[6 + m], xi[6 + m], -w.z2ai, w.z2ar);
+        bf(xr[8 + m], xi[8 + m], xr[10 + m], xi[10 + m], w.z2br, w.z2bi);
+        bf(xr[12 + m], xi[12 + m], xr[14 + m], xi[14 + m], -w.z2bi, w.z2br);
+    }
+    bf(xr[0], xi[0], xr[1], xi[1], w.z1ar, w.z1ai);
+    bf(xr[2], xi[2], xr[3], xi[3], -w.z1ai, w.z1ar);
+    bf(xr[4], xi[4], xr[5], xi[5], w.z1aqr, w.z1aqi);
+    bf(xr[6], xi[6], xr[7], xi[7], -w.z1aqi, w.z1aqr);
+    bf(xr[8], xi[8], xr[9], xi[9], w.z1br, w.z1bi);
+    bf(xr[10], xi[10], xr[11], xi[11], -w.z1bi, w.z1br);
+    bf(xr[12], xi[12], xr[13], xi[13], w.z1bqr, w.z1bqi);
+    bf(xr[14], xi[14], xr[15], xi[15], -w.z1bqi, w.z1bqr);
+}
+/* uniform final stage: y[s] <- keep + w recv, y[8+s] <- keep - w recv with keep = y[s]; recv is the partner's y[8+s] */
+IE_HD void fin_fwd_apply_folded(double (&yr)[16], double (&yi)[16], const double (&rr)[8], const double (&ri)[8],
+                                const double (&wr)[8], const double (&wi)[8])
+{
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+        double br = rr[s], bi = ri[s];
+        bf(yr[s], yi[s], br, bi, wr[s], wi[s]);
+        yr[8 + s] = br; yi[8 + s] = bi;
+    }
+}
+
 /* evaluation index of register p (0..15) of lane l */
 IE_HD int warp_slot_to_K(int p, int lane)
 {
@@ -204,6 +250,37 @@ inline void host_twiddles_warp(Tw16 *tw2 /*16*/, FinTw *fin /*32*/)
             const long double phi = pi * (1 + 4 * brev4(lane & 15) + 64 * brev4(s + 8 * (lane >> 4))) / 1024.0L;
             fin[lane].zr[s] = (double)cosl(phi); fin[lane].zi[s] = (double)sinl(phi);
         }
+}
+
+/* host-side tables of the folded variant: pass-2 twiddles per LANE, final-stage w per lane, and the factor that the
+ * key layout multiplies into slot p of lane l (1 for Lpar = 0) */
+inline void host_twiddles_warp_folded(Tw16g *tw2 /*32*/, FinTw *fin /*32*/)
+{
+    const long double pi = 3.14159265358979323846264338327950288L;
+    for (int lane = 0; lane < 32; lane++) {
+        const Tw16 t = make_tw16(pi * (1 + 4 * brev4(lane & 15)) / 512.0L);
+        Tw16g g;
+        const bool sw = (lane >> 4) != 0;
+        g.z8r = sw ? -t.z8r : t.z8r; g.z8i = sw ? -t.z8i : t.z8i;
+        /* block twiddles: natural lanes give block a = (z4, z2, z1, z1q) and block b = (i z4, z2q, z1h, z1hq) */
+        const double a4r = t.z4r, a4i = t.z4i, b4r = -t.z4i, b4i = t.z4r;
+        g.z4ar = sw ? b4r : a4r; g.z4ai = sw ? b4i : a4i; g.z4br = sw ? a4r : b4r; g.z4bi = sw ? a4i : b4i;
+        g.z2ar = sw ? t.z2qr : t.z2r; g.z2ai = sw ? t.z2qi : t.z2i; g.z2br = sw ? t.z2r : t.z2qr; g.z2bi = sw ? t.z2i : t.z2qi;
+        g.z1ar = sw ? t.z1hr : t.z1r; g.z1ai = sw ? t.z1hi : t.z1i; g.z1aqr = sw ? t.z1hqr : t.z1qr; g.z1aqi = sw ? t.z1hqi : t.z1qi;
+        g.z1br = sw ? t.z1r : t.z1hr; g.z1bi = sw ? t.z1i : t.z1hi; g.z1bqr = sw ? t.z1qr : t.z1hqr; g.z1bqi = sw ? t.z1qi : t.z1hqi;
+        tw2[lane] = g;
+        for (int s = 0; s < 8; s++) {
+            const long double phi = pi * (1 + 4 * brev4(lane & 15) + 64 * brev4(s + 8 * (lane >> 4))) / 1024.0L;
+            fin[lane].zr[s] = (double)cosl(phi); fin[lane].zi[s] = sw ? -(double)sinl(phi) : (double)sinl(phi);
+        }
+    }
+}
+/* factor of key slot p (0..15) of lane l in the folded layout: Y for p < 8, -Y for p >= 8 on Lpar = 1 lanes, Y = conj(fin w) */
+IE_HD void folded_bk_factor(const FinTw &fin_lane, int p, int lane, double &fr, double &fi)
+{
+    if ((lane >> 4) == 0) { fr = 1.0; fi = 0.0; return; }
+    const double yr = fin_lane.zr[p & 7], yi = -fin_lane.zi[p & 7];
+    fr = (p < 8) ? yr : -yr; fi = (p < 8) ? yi : -yi;
 }
 
 } // namespace ieache

@@ -246,6 +246,7 @@ struct ieache_cloudkey {
     DevParams dp{};
     double2 *bkfft = nullptr; size_t bkfft_bytes = 0;
     mutable double2 *bkfft_w = nullptr;                /* warp-per-gate layout of the same values, made on first use */
+    mutable int bkfft_w_kind = 0;                      /* 1 plain, 2 folded (unit factors of variant 61 multiplied in) */
     int32_t *ksk = nullptr; size_t ksk_bytes = 0;
     bool owns = true;
 };
@@ -493,11 +494,13 @@ static int run_br(ieache_ctx *ctx, const ieache_cloudkey *key, const GateAddr &g
     TimedLaunch t{};
     { int rcp = apply_l2_persist(ctx, key); if (rcp) return rcp; }
     if (ctx->timing) { CU(cudaEventCreate(&t.a)); CU(cudaEventCreate(&t.b)); t.kind = 0; CU(cudaEventRecord(t.a, ctx->stream)); }
-    if (!key->bkfft_w && blind_rotate_uses_warp_layout((long long)ga.ntempl * ga.n_inst)) {
-        CU(cudaMalloc((void **)&key->bkfft_w, key->bkfft_bytes));
-        CU(launch_bk_relayout_warp(key->bkfft, key->bkfft_w, (int)(key->bkfft_bytes / (kHalfNBytes)), ctx->stream));
+    const int want_layout = blind_rotate_warp_layout((long long)ga.ntempl * ga.n_inst);
+    if (want_layout && key->bkfft_w_kind != want_layout) {
+        if (!key->bkfft_w) CU(cudaMalloc((void **)&key->bkfft_w, key->bkfft_bytes));
+        CU(launch_bk_relayout_warp(key->bkfft, key->bkfft_w, (int)(key->bkfft_bytes / (kHalfNBytes)), want_layout == 2, ctx->stream));
+        key->bkfft_w_kind = want_layout;
     }
-    CU(launch_blind_rotate(key->dp, key->bkfft, key->bkfft_w, ga, A, B, ext ? ext : ctx->d_ext, ext_base, ctx->stream));
+    CU(launch_blind_rotate(key->dp, key->bkfft, want_layout ? key->bkfft_w : nullptr, ga, A, B, ext ? ext : ctx->d_ext, ext_base, ctx->stream));
     if (ctx->timing) { CU(cudaEventRecord(t.b, ctx->stream)); ctx->timed.push_back(t); }
     ctx->launches++;
     return IEACHE_OK;

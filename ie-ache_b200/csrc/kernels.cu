@@ -30,6 +30,8 @@ __device__ Tw d_tw2[8];
 __device__ Tw d_tw3[64];
 __device__ Tw16 d_tw16[16];   /* warp layout: pass-2 twiddles by lane & 15 */
 __device__ FinTw d_fin[32];   /* warp layout: final-stage twiddles by lane */
+__device__ Tw16g d_tw16g[32]; /* folded forward variant: pass-2 twiddles by lane */
+__device__ FinTw d_finf[32];  /* folded forward variant: final-stage w by lane */
 
 cudaError_t upload_twiddles()
 {
@@ -43,6 +45,13 @@ cudaError_t upload_twiddles()
     e = cudaMemcpyToSymbol(d_tw16, tw16, sizeof(tw16));
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbol(d_fin, fin, sizeof(fin));
+    if (e != cudaSuccess) return e;
+    Tw16g tw16g[32];
+    FinTw finf[32];
+    host_twiddles_warp_folded(tw16g, finf);
+    e = cudaMemcpyToSymbol(d_tw16g, tw16g, sizeof(tw16g));
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbol(d_finf, finf, sizeof(finf));
     if (e != cudaSuccess) return e;
     return cudaMemcpyToSymbol(d_tw3, tw3, sizeof(tw3));
 }
@@ -514,17 +523,24 @@ static cudaError_t launch_br_tmem(const DevParams &p, const double2 *bkfft, cons
  * that bk_relayout_warp_kernel derives from the [slot 8][thread 64] one at key load (same values, permuted). */
 constexpr int kWarpGateSmem = kAccBytes + kWarpBufElems * 16 + kAbarBytes; /* 18 720 B per gate */
 
-__global__ void __launch_bounds__(512) bk_relayout_warp_kernel(const double2 *__restrict__ old, double2 *__restrict__ neu, int npoly)
+__global__ void __launch_bounds__(512) bk_relayout_warp_kernel(const double2 *__restrict__ old, double2 *__restrict__ neu, int npoly, int folded)
 {
     const int q = blockIdx.x, idx = threadIdx.x;
     if (q >= npoly) return;
-    const int K = warp_slot_to_K(idx >> 5, idx & 31);
+    const int p = idx >> 5, lane = idx & 31;
+    const int K = warp_slot_to_K(p, lane);
     const int t3 = 8 * (K & 7) + ((K >> 3) & 7), r8 = brev3(K >> 6); /* br_core.h: K = b + 8k' + 64 brev3(r), t3 = 8b + k' */
-    neu[(size_t)q * kHalfN + idx] = old[(size_t)q * kHalfN + r8 * 64 + t3];
+    double2 v = old[(size_t)q * kHalfN + r8 * 64 + t3];
+    if (folded) { /* the unit factor the select-free forward transform leaves on the Lpar = 1 lanes (br_warp.h) */
+        double fr, fi;
+        folded_bk_factor(d_finf[lane], p, lane, fr, fi);
+        v = make_double2(v.x * fr - v.y * fi, v.x * fi + v.y * fr);
+    }
+    neu[(size_t)q * kHalfN + idx] = v;
 }
-cudaError_t launch_bk_relayout_warp(const double2 *bkfft, double2 *bkfft_w, int npoly, cudaStream_t s)
+cudaError_t launch_bk_relayout_warp(const double2 *bkfft, double2 *bkfft_w, int npoly, int folded, cudaStream_t s)
 {
-    bk_relayout_warp_kernel<<<npoly, 512, 0, s>>>(bkfft, bkfft_w, npoly);
+    bk_relayout_warp_kernel<<<npoly, 512, 0, s>>>(bkfft, bkfft_w, npoly, folded);
     return cudaGetLastError();
 }
 
@@ -534,7 +550,7 @@ __device__ __forceinline__ void warp_exchange8(const double (&sr)[8], const doub
     for (int s = 0; s < 8; s++) { rr[s] = __shfl_xor_sync(0xffffffffu, sr[s], 16); ri[s] = __shfl_xor_sync(0xffffffffu, si[s], 16); }
 }
 
-template <int L>
+template <int L, bool FOLD = false>
 __global__ void __launch_bounds__(128, 2)
 blind_rotate_warp_kernel(DevParams p, const double2 *__restrict__ bkw, GateAddr ga, const int32_t *__restrict__ baseA,
                          const int32_t *__restrict__ baseB, int32_t *__restrict__ ext)
@@ -543,9 +559,20 @@ blind_rotate_warp_kernel(DevParams p, const double2 *__restrict__ bkw, GateAddr 
     __shared__ uint32_t tmem_base_slot;
     __shared__ double s_finr[8][32], s_fini[8][32]; /* final-stage twiddles [s][lane]: 32 registers per thread otherwise */
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, lpar = lane >> 4;
+    __shared__ double s_finfr[FOLD ? 8 : 1][32], s_finfi[FOLD ? 8 : 1][32]; /* folded variant: forward-stage w */
+    __shared__ double s_tw2[FOLD ? 16 : 1][16];                             /* folded variant: plain pass-2 twiddles for the inverse */
     if (warp == 1) {
 #pragma unroll
         for (int s8 = 0; s8 < 8; s8++) { s_finr[s8][lane] = d_fin[lane].zr[s8]; s_fini[s8][lane] = d_fin[lane].zi[s8]; }
+        if (FOLD) {
+#pragma unroll
+            for (int s8 = 0; s8 < 8; s8++) { s_finfr[s8][lane] = d_finf[lane].zr[s8]; s_finfi[s8][lane] = d_finf[lane].zi[s8]; }
+        }
+    }
+    if (FOLD && warp == 2 && lane < 16) {
+        const double *src = reinterpret_cast<const double *>(&d_tw16[lane]);
+#pragma unroll
+        for (int v = 0; v < 16; v++) s_tw2[v][lane] = src[v];
     }
     unsigned char *base = smem_raw + (size_t)warp * kWarpGateSmem;
     int32_t *acc = reinterpret_cast<int32_t *>(base);
@@ -589,7 +616,8 @@ blind_rotate_warp_kernel(DevParams p, const double2 *__restrict__ bkw, GateAddr 
     __syncwarp();
 
     const Tw16 w1 = tw16_pass1();
-    const Tw16 w2 = d_tw16[lane & 15];
+    const Tw16 w2 = d_tw16[FOLD ? 0 : (lane & 15)]; /* FOLD: unused (the forward uses w2g, the inverse reloads from shared memory) */
+    const Tw16g w2g = d_tw16g[FOLD ? lane : 0];
     const int Bgbit = p.Bgbit;
     const uint32_t maskBg = (1u << Bgbit) - 1;
     const int32_t halfBg = 1 << (Bgbit - 1);
@@ -621,8 +649,19 @@ blind_rotate_warp_kernel(DevParams p, const double2 *__restrict__ bkw, GateAddr 
                 st16_pass1(buf, lane, xr, xi);
                 __syncwarp();
                 ld16_pass2(buf, lane, xr, xi);
-                pass16_fwd(xr, xi, w2);
-                {
+                if (FOLD) {
+                    /* select-free form: both lanes of a pair send registers 8..15, keep 0..7 and compute keep +- w recv;
+                     * the unit factors this leaves on the Lpar = 1 lanes are in the key layout (br_warp.h) */
+                    pass16_fwd_g(xr, xi, w2g);
+                    double sr[8], si[8], rr[8], ri[8], fzr[8], fzi[8];
+#pragma unroll
+                    for (int s8 = 0; s8 < 8; s8++) { sr[s8] = xr[8 + s8]; si[s8] = xi[8 + s8]; }
+                    warp_exchange8(sr, si, rr, ri);
+#pragma unroll
+                    for (int s8 = 0; s8 < 8; s8++) { fzr[s8] = s_finfr[s8][lane]; fzi[s8] = s_finfi[s8][lane]; }
+                    fin_fwd_apply_folded(xr, xi, rr, ri, fzr, fzi);
+                } else {
+                    pass16_fwd(xr, xi, w2);
                     double sr[8], si[8], rr[8], ri[8], fzr[8], fzi[8];
                     fin_fwd_send(xr, xi, lpar, sr, si);
                     warp_exchange8(sr, si, rr, ri);
@@ -687,7 +726,15 @@ blind_rotate_warp_kernel(DevParams p, const double2 *__restrict__ bkw, GateAddr 
                 warp_exchange8(sr, si, rr, ri);
                 fin_inv_place(xr, xi, lpar, rr, ri);
             }
-            pass16_inv(xr, xi, w2);
+            if (FOLD) {
+                Tw16 wi;
+                double *dst = reinterpret_cast<double *>(&wi);
+#pragma unroll
+                for (int v = 0; v < 16; v++) dst[v] = s_tw2[v][lane & 15];
+                pass16_inv(xr, xi, wi);
+            } else {
+                pass16_inv(xr, xi, w2);
+            }
             __syncwarp();
             st16_ipass2(buf, lane, xr, xi);
             __syncwarp();
@@ -713,14 +760,14 @@ blind_rotate_warp_kernel(DevParams p, const double2 *__restrict__ bkw, GateAddr 
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem_base_slot));
 }
 
-template <int L>
+template <int L, bool FOLD>
 static cudaError_t launch_br_warp(const DevParams &p, const double2 *bkw, const GateAddr &ga, const int32_t *baseA,
                                   const int32_t *baseB, int32_t *ext, long long count, cudaStream_t s)
 {
     constexpr int smem = 4 * kWarpGateSmem;
-    cudaError_t e = cudaFuncSetAttribute(blind_rotate_warp_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(blind_rotate_warp_kernel<L, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    blind_rotate_warp_kernel<L><<<(int)((count + 3) / 4), 128, smem, s>>>(p, bkw, ga, baseA, baseB, ext);
+    blind_rotate_warp_kernel<L, FOLD><<<(int)((count + 3) / 4), 128, smem, s>>>(p, bkw, ga, baseA, baseB, ext);
     return cudaGetLastError();
 }
 
@@ -1114,9 +1161,10 @@ static cudaError_t launch_br_variant(const DevParams &p, const double2 *bkfft, c
     return cudaGetLastError();
 }
 
-bool blind_rotate_uses_warp_layout(long long count)
+int blind_rotate_warp_layout(long long count) /* 0 = not needed, 1 = plain warp layout, 2 = folded (variant 61) */
 {
-    return br_variant() == 60 && count > 0;
+    if (count <= 0) return 0;
+    return br_variant() == 60 ? 1 : (br_variant() == 61 ? 2 : 0);
 }
 
 cudaError_t launch_blind_rotate(const DevParams &p, const double2 *bkfft, const double2 *bkfft_w, const GateAddr &ga, const int32_t *baseA,
@@ -1145,8 +1193,12 @@ cudaError_t launch_blind_rotate(const DevParams &p, const double2 *bkfft, const 
         if (p.l == 2) return launch_br_pair<2>(p, bkfft, ga, baseA, baseB, ext, count, s);
     }
     if (bkfft_w && br_variant() == 60) {
-        if (p.l == 3) return launch_br_warp<3>(p, bkfft_w, ga, baseA, baseB, ext, count, s);
-        if (p.l == 2) return launch_br_warp<2>(p, bkfft_w, ga, baseA, baseB, ext, count, s);
+        if (p.l == 3) return launch_br_warp<3, false>(p, bkfft_w, ga, baseA, baseB, ext, count, s);
+        if (p.l == 2) return launch_br_warp<2, false>(p, bkfft_w, ga, baseA, baseB, ext, count, s);
+    }
+    if (bkfft_w && br_variant() == 61) {
+        if (p.l == 3) return launch_br_warp<3, true>(p, bkfft_w, ga, baseA, baseB, ext, count, s);
+        if (p.l == 2) return launch_br_warp<2, true>(p, bkfft_w, ga, baseA, baseB, ext, count, s);
     }
     if (p.l == 2) return launch_br_variant<2, 1, 4, 2>(p, bkfft, ga, baseA, baseB, ext, count, s);
     if (p.l != 3) return cudaErrorInvalidValue;

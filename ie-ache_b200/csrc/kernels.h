@@ -58,11 +58,11 @@ cudaError_t launch_bk_fft(const int32_t *bk_coef, double2 *bkfft, int npoly, cud
 /* bkfft_w: the same key in the warp-per-gate layout [row][poly][slot 16][lane 32] (launch_bk_relayout_warp), or nullptr */
 cudaError_t launch_blind_rotate(const DevParams &p, const double2 *bkfft, const double2 *bkfft_w, const GateAddr &ga, const int32_t *baseA,
                                 const int32_t *baseB, int32_t *ext, int ext_base, cudaStream_t s);
-bool blind_rotate_uses_warp_layout(long long count);
+int blind_rotate_warp_layout(long long count); /* which layout the selected variant reads: 0 none, 1 plain, 2 folded */
 /* which compiled variant of the throughput blind rotation wide launches use (41 = default register kernel, 60 = one
  * warp per gate with TMEM accumulators, 51/52/55/56 = TMEM accumulators with 64-thread groups, ...); returns the old one */
 int set_throughput_variant(int v);
-cudaError_t launch_bk_relayout_warp(const double2 *bkfft, double2 *bkfft_w, int npoly, cudaStream_t s);
+cudaError_t launch_bk_relayout_warp(const double2 *bkfft, double2 *bkfft_w, int npoly, int folded, cudaStream_t s);
 /* key switch of ext[g] (+ ext[g + pair_offset] if pair_offset > 0) + (0, cst_post) into sample out of out_base */
 cudaError_t launch_keyswitch(const DevParams &p, const int32_t *ksk, const GateAddr &ga, int32_t *out_base,
                              const int32_t *ext, int pair_offset, int32_t cst_post, cudaStream_t s);

@@ -270,3 +270,42 @@ void emul_warp_blind_rotate(int n, int l, int Bgbit, int32_t mu, const int32_t *
 }
 
 } // extern "C"
+
+/* ------------------------------------------------------------------ folded forward variant of the warp layout */
+namespace {
+struct EmulWF {
+    Tw16 w1;
+    Tw16g w2[32];
+    FinTw fin[32];
+    EmulWF() { w1 = tw16_pass1(); host_twiddles_warp_folded(w2, fin); }
+    void fwd(Regs16 *t, cd *buf) const
+    {
+        for (int l = 0; l < 32; l++) { pass16_fwd(t[l].xr, t[l].xi, w1); st16_pass1(buf, l, t[l].xr, t[l].xi); }
+        for (int l = 0; l < 32; l++) { ld16_pass2(buf, l, t[l].xr, t[l].xi); pass16_fwd_g(t[l].xr, t[l].xi, w2[l]); }
+        double sr[32][8], si[32][8];
+        for (int l = 0; l < 32; l++) for (int s = 0; s < 8; s++) { sr[l][s] = t[l].xr[8 + s]; si[l][s] = t[l].xi[8 + s]; }
+        for (int l = 0; l < 32; l++) fin_fwd_apply_folded(t[l].xr, t[l].xi, sr[l ^ 16], si[l ^ 16], fin[l].zr, fin[l].zi);
+    }
+};
+const EmulWF &emulwf() { static EmulWF e; return e; }
+} // namespace
+
+extern "C" {
+/* forward transform of the folded variant, multiplied back by the key factor: must equal the plain warp layout */
+void emul_warpf_fft_unfolded(const int32_t *coef, double *out /*512*2*/)
+{
+    const EmulWF &e = emulwf();
+    Regs16 t[32];
+    cd buf[kWarpBufElems];
+    for (int l = 0; l < 32; l++)
+        for (int m = 0; m < 16; m++) { t[l].xr[m] = (double)coef[l + 32 * m]; t[l].xi[m] = (double)coef[l + 32 * m + 512]; }
+    e.fwd(t, buf);
+    for (int l = 0; l < 32; l++)
+        for (int p = 0; p < 16; p++) {
+            double fr, fi;
+            folded_bk_factor(e.fin[l], p, l, fr, fi);
+            out[2 * (p * 32 + l)] = t[l].xr[p] * fr - t[l].xi[p] * fi;
+            out[2 * (p * 32 + l) + 1] = t[l].xr[p] * fi + t[l].xi[p] * fr;
+        }
+}
+} // extern "C"

@@ -141,3 +141,14 @@ def test_warp_blind_rotate_matches_oracle(emul, oracle, n, l, bgbit):
         d = ((d + 2 ** 31) % 2 ** 32) - 2 ** 31
         assert np.abs(d).max() <= 2
     ks.free()
+
+
+def test_warp_folded_forward_equals_plain_after_key_factor(emul):
+    """the select-free forward variant leaves the Lpar = 1 lanes' results scaled by unit factors that the key layout
+    carries: multiplied back, it must reproduce the plain warp-layout spectrum"""
+    rng = np.random.default_rng(21)
+    a = rng.integers(-64, 64, 1024).astype(np.int32)
+    plain, folded = np.zeros(1024), np.zeros(1024)
+    emul.emul_warp_fft(vp(a), vp(plain), ctypes.c_double(1.0))
+    emul.emul_warpf_fft_unfolded(vp(a), vp(folded))
+    assert np.abs(plain - folded).max() < 1e-9
