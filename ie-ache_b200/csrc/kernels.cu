@@ -273,7 +273,18 @@ __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__
                 }
                 cd *buf = toggle ? bufB : bufA;
                 toggle ^= 1;
-                fwd_transform(xr, xi, buf, tid, bar, w1, w2, w3);
+                if (NOBK == 3) { /* timing experiment (wrong results): forward transform without the butterflies of pass 2 */
+                    pass_fwd(xr, xi, w1);
+                    st_pass1(buf, tid, xr, xi);
+                    group_sync(bar);
+                    ld_pass2(buf, tid, xr, xi);
+                    st_pass2(buf, tid, xr, xi);
+                    group_sync(bar);
+                    ld_pass3(buf, tid, xr, xi);
+                    pass_fwd(xr, xi, w3);
+                } else {
+                    fwd_transform(xr, xi, buf, tid, bar, w1, w2, w3);
+                }
 #pragma unroll
                 for (int r = 0; r < 8; r++) {
                     /* NOBK (timing experiments, wrong results): 1 = no loads at all, 2 = the same 16-byte loads from a
@@ -1232,6 +1243,7 @@ cudaError_t launch_blind_rotate(const DevParams &p, const double2 *bkfft, const 
     case 107: return launch_br_variant<3, 1, 4, 0, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
     case 40: return launch_br_variant<3, 1, 4, 2, 0, false, false, true>(p, bkfft, ga, baseA, baseB, ext, count, s); /* ACC in registers */
     case 41: return launch_br_variant<3, 1, 4, 0, 0, false, false, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case 307: return launch_br_variant<3, 1, 4, 0, 3, false, false, true>(p, bkfft, ga, baseA, baseB, ext, count, s); /* -19 % FP64, same LSU */
     case 207: return launch_br_variant<3, 1, 4, 2, 2>(p, bkfft, ga, baseA, baseB, ext, count, s);
     case 208: return launch_br_variant<3, 1, 5, 2, 2>(p, bkfft, ga, baseA, baseB, ext, count, s);
     case 109: return launch_br_variant<3, 1, 6, 0, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
