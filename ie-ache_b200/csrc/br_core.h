@@ -92,6 +92,36 @@ IE_HD void pass_inv(double (&xr)[8], double (&xi)[8], const Tw &w)
     for (int m = 0; m < 4; m++) ibf(xr[m], xi[m], xr[m + 4], xi[m + 4], w.s4r, w.s4i);
 }
 
+/* Pass 1 of a forward transform straight from the integer gadget digits.  Its first stage multiplies by
+ * s^4 = (1 + i)/sqrt 2, so a + s^4 b = (a_r + c (b_r - b_i)) + i (a_i + c (b_r + b_i)) with c = 1/sqrt 2: taking the
+ * difference and the sum of the two small integers before the conversion leaves 4 FMAs per butterfly instead of 6
+ * (48 fewer FP64 instructions per CMux step and thread).  dr[m], di[m]: digits of coefficients m and m+8 of the 16
+ * a thread owns (the real and imaginary part of its point m). */
+IE_HD void pass1_fwd_from_digits(const int32_t (&dr)[8], const int32_t (&di)[8], double (&xr)[8], double (&xi)[8], const Tw &w)
+{
+    const double c = 0.70710678118654752440;
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        const double ar = (double)dr[m], ai = (double)di[m];
+        const double u = (double)(dr[m + 4] - di[m + 4]), v = (double)(dr[m + 4] + di[m + 4]);
+        xr[m] = fma(c, u, ar); xi[m] = fma(c, v, ai);
+        xr[m + 4] = fma(-c, u, ar); xi[m + 4] = fma(-c, v, ai);
+    }
+    bf(xr[0], xi[0], xr[2], xi[2], w.s2r, w.s2i);
+    bf(xr[1], xi[1], xr[3], xi[3], w.s2r, w.s2i);
+    bf(xr[4], xi[4], xr[6], xi[6], -w.s2i, w.s2r);
+    bf(xr[5], xi[5], xr[7], xi[7], -w.s2i, w.s2r);
+    bf(xr[0], xi[0], xr[1], xi[1], w.s1r, w.s1i);
+    bf(xr[2], xi[2], xr[3], xi[3], -w.s1i, w.s1r);
+    bf(xr[4], xi[4], xr[5], xi[5], w.sqr, w.sqi);
+    bf(xr[6], xi[6], xr[7], xi[7], -w.sqi, w.sqr);
+}
+/* digit p of the signed base-2^Bgbit decomposition as an integer */
+IE_HD int32_t digit_i32(int32_t c, uint32_t offset, int shift, uint32_t mask, int32_t halfBg)
+{
+    return (int32_t)((((uint32_t)c + offset) >> shift) & mask) - halfBg;
+}
+
 IE_HD int brev3(int r) { return ((r & 1) << 2) | (r & 2) | ((r >> 2) & 1); }
 
 /* pass-1 twiddles: s = exp(i pi/16), identical for every thread */

@@ -88,6 +88,20 @@ __device__ __forceinline__ void fwd_transform(double (&xr)[8], double (&xi)[8], 
     ld_pass3(buf, tid, xr, xi);
     pass_fwd(xr, xi, w3);
 }
+/* same, starting from the integer digits (pass 1 with the cheaper first stage, br_core.h) */
+__device__ __forceinline__ void fwd_transform_digits(const int32_t (&dr)[8], const int32_t (&di)[8], double (&xr)[8], double (&xi)[8],
+                                                     cd *buf, int tid, int grp, const Tw &w1, const Tw &w2, const Tw &w3)
+{
+    pass1_fwd_from_digits(dr, di, xr, xi, w1);
+    st_pass1(buf, tid, xr, xi);
+    group_sync(grp);
+    ld_pass2(buf, tid, xr, xi);
+    pass_fwd(xr, xi, w2);
+    st_pass2(buf, tid, xr, xi);
+    group_sync(grp);
+    ld_pass3(buf, tid, xr, xi);
+    pass_fwd(xr, xi, w3);
+}
 /* inverse (x512): evaluations in x[r] -> z[tid+64m] in x[m] */
 __device__ __forceinline__ void inv_transform(double (&xr)[8], double (&xi)[8], cd *buf, int tid, int grp,
                                               const Tw &w1, const Tw &w2, const Tw &w3)
@@ -266,13 +280,22 @@ __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__
             for (int pp = 0; pp < L; pp++) {
                 const int shift = 32 - (pp + 1) * Bgbit;
                 double xr[8], xi[8];
+                cd *buf = toggle ? bufB : bufA;
+                toggle ^= 1;
+                if (ACCREG) { /* the default variant also starts the transform from the integer digits */
+                    int32_t dr[8], di[8];
+#pragma unroll
+                    for (int m = 0; m < 8; m++) {
+                        dr[m] = digit_i32(c[m], offset, shift, maskBg, halfBg);
+                        di[m] = digit_i32(c[8 + m], offset, shift, maskBg, halfBg);
+                    }
+                    fwd_transform_digits(dr, di, xr, xi, buf, tid, bar, w1, w2, w3);
+                } else {
 #pragma unroll
                 for (int m = 0; m < 8; m++) {
                     xr[m] = digit_f64(c[m], offset, shift, maskBg, halfBg);
                     xi[m] = digit_f64(c[8 + m], offset, shift, maskBg, halfBg);
                 }
-                cd *buf = toggle ? bufB : bufA;
-                toggle ^= 1;
                 if (NOBK == 3) { /* timing experiment (wrong results): forward transform without the butterflies of pass 2 */
                     pass_fwd(xr, xi, w1);
                     st_pass1(buf, tid, xr, xi);
@@ -284,6 +307,7 @@ __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__
                     pass_fwd(xr, xi, w3);
                 } else {
                     fwd_transform(xr, xi, buf, tid, bar, w1, w2, w3);
+                }
                 }
 #pragma unroll
                 for (int r = 0; r < 8; r++) {

@@ -109,12 +109,21 @@ void emul_blind_rotate(int n, int l, int Bgbit, int32_t mu, const int32_t *bk_co
             for (int tid = 0; tid < 64; tid++) rot_minus_one(&acc[q * kN], tid, a, c[tid]);
             for (int pp = 0; pp < l; pp++) {
                 const int shift = 32 - (pp + 1) * Bgbit;
-                for (int tid = 0; tid < 64; tid++)
-                    for (int m = 0; m < 8; m++) {
-                        t[tid].xr[m] = digit_f64(c[tid][m], offset, shift, maskBg, halfBg);
-                        t[tid].xi[m] = digit_f64(c[tid][8 + m], offset, shift, maskBg, halfBg);
+                {   /* as the default kernel: pass 1 straight from the integer digits, then passes 2 and 3 */
+                    cd *buf = toggle ? bufB : bufA; toggle ^= 1;
+                    for (int tid = 0; tid < 64; tid++) {
+                        int32_t dr[8], di[8];
+                        for (int m = 0; m < 8; m++) {
+                            dr[m] = digit_i32(c[tid][m], offset, shift, maskBg, halfBg);
+                            di[m] = digit_i32(c[tid][8 + m], offset, shift, maskBg, halfBg);
+                        }
+                        pass1_fwd_from_digits(dr, di, t[tid].xr, t[tid].xi, e.w1);
+                        st_pass1(buf, tid, t[tid].xr, t[tid].xi);
                     }
-                e.fwd(t, toggle ? bufB : bufA); toggle ^= 1;
+                    for (int tid = 0; tid < 64; tid++) ld_pass2(buf, tid, t[tid].xr, t[tid].xi);
+                    for (int tid = 0; tid < 64; tid++) { pass_fwd(t[tid].xr, t[tid].xi, e.w2[tid >> 3]); st_pass2(buf, tid, t[tid].xr, t[tid].xi); }
+                    for (int tid = 0; tid < 64; tid++) { ld_pass3(buf, tid, t[tid].xr, t[tid].xi); pass_fwd(t[tid].xr, t[tid].xi, e.w3[tid]); }
+                }
                 const double *bk_r = &bkfft[(((size_t)i * kpl + q * l + pp) * 2) * 1024];
                 for (int tid = 0; tid < 64; tid++)
                     for (int j = 0; j < 2; j++)
