@@ -109,6 +109,22 @@ def cpu_port_rate(seconds_budget: float, threads: int = 0):
     return done / dt, threads, done, dt
 
 
+def cpu_port_single_thread_ms(n_gates: int = 100) -> float:
+    """one host thread, mean over n_gates bootstrapped NAND gates of the oracle, in ms per gate"""
+    import oracle_bind as ob
+    orc = ob.Oracle()
+    ks = orc.keygen(ob.params_default(N_LWE), seed=2025)
+    rng = np.random.default_rng(4)
+    a = ks.encrypt(rng.integers(0, 2, n_gates).astype(np.int32), 1)
+    b = ks.encrypt(rng.integers(0, 2, n_gates).astype(np.int32), 2)
+    ks.gate_batch(ob.OPS["NAND"], a[:2], b[:2], threads=1)
+    t0 = time.perf_counter()
+    ks.gate_batch(ob.OPS["NAND"], a, b, threads=1)
+    dt = time.perf_counter() - t0
+    ks.free()
+    return 1e3 * dt / n_gates
+
+
 def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
@@ -426,7 +442,8 @@ def main():
     if rank == 0 and world == 1:
         r, threads, done, dt = cpu_port_rate(args.cpu_seconds)
         cpu = {"value": r, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{done} independent bootsNAND in {dt:.1f} s on {threads} threads (oracle/: C restatement of libtfhe, default parameters)"}
+               "sample": f"{done} independent bootsNAND in {dt:.1f} s on {threads} threads (oracle/: C restatement of libtfhe, default parameters)",
+               "single_thread_ms_per_gate": cpu_port_single_thread_ms(100 if args.cpu_seconds >= 5 else 10)}
 
     if rank == 0:
         line = {
