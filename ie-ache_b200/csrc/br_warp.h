@@ -57,6 +57,49 @@ IE_HD void pass16_fwd(double (&xr)[16], double (&xi)[16], const Tw16 &w)
     bf(xr[12], xi[12], xr[13], xi[13], w.z1hqr, w.z1hqi);
     bf(xr[14], xi[14], xr[15], xi[15], -w.z1hqi, w.z1hqr);
 }
+/* stages 2..4 of pass16_fwd (everything after the m / m+8 butterflies) */
+IE_HD void pass16_fwd_tail(double (&xr)[16], double (&xi)[16], const Tw16 &w)
+{
+#pragma unroll
+    for (int m = 0; m < 4; m++) bf(xr[m], xi[m], xr[m + 4], xi[m + 4], w.z4r, w.z4i);
+#pragma unroll
+    for (int m = 8; m < 12; m++) bf(xr[m], xi[m], xr[m + 4], xi[m + 4], -w.z4i, w.z4r);
+#pragma unroll
+    for (int m = 0; m < 2; m++) {
+        bf(xr[m], xi[m], xr[m + 2], xi[m + 2], w.z2r, w.z2i);
+        bf(xr[4 + m], xi[4 + m], xr[6 + m], xi[6 + m], -w.z2i, w.z2r);
+        bf(xr[8 + m], xi[8 + m], xr[10 + m], xi[10 + m], w.z2qr, w.z2qi);
+        bf(xr[12 + m], xi[12 + m], xr[14 + m], xi[14 + m], -w.z2qi, w.z2qr);
+    }
+    bf(xr[0], xi[0], xr[1], xi[1], w.z1r, w.z1i);
+    bf(xr[2], xi[2], xr[3], xi[3], -w.z1i, w.z1r);
+    bf(xr[4], xi[4], xr[5], xi[5], w.z1qr, w.z1qi);
+    bf(xr[6], xi[6], xr[7], xi[7], -w.z1qi, w.z1qr);
+    bf(xr[8], xi[8], xr[9], xi[9], w.z1hr, w.z1hi);
+    bf(xr[10], xi[10], xr[11], xi[11], -w.z1hi, w.z1hr);
+    bf(xr[12], xi[12], xr[13], xi[13], w.z1hqr, w.z1hqi);
+    bf(xr[14], xi[14], xr[15], xi[15], -w.z1hqi, w.z1hqr);
+}
+/* Pass 1 of a forward transform straight from the gadget digits (the 16-point form of br_core.h's
+ * pass1_fwd_from_digits).  cc[h] = coefficient + decomposition offset, h = m for the real part of point m and 16 + m
+ * for its imaginary part; digit = ((cc >> shift) & mask) - half.  The first stage multiplies by (1 + i)/sqrt 2, so the
+ * difference and the sum of the two small integers are taken before the conversion: 4 FMAs per butterfly instead of
+ * 6, and the -half of the two digits cancels in the difference. */
+IE_HD void pass16_fwd_from_digits(const uint32_t (&cc)[32], int shift, uint32_t mask, int32_t half, double (&xr)[16], double (&xi)[16],
+                                  const Tw16 &w)
+{
+    const double c = 0.70710678118654752440;
+#pragma unroll
+    for (int m = 0; m < 8; m++) {
+        const int32_t ar_i = (int32_t)((cc[m] >> shift) & mask) - half, ai_i = (int32_t)((cc[16 + m] >> shift) & mask) - half;
+        const int32_t br_i = (int32_t)((cc[m + 8] >> shift) & mask), bi_i = (int32_t)((cc[24 + m] >> shift) & mask);
+        const double ar = (double)ar_i, ai = (double)ai_i;
+        const double u = (double)(br_i - bi_i), v = (double)(br_i + bi_i - 2 * half);
+        xr[m] = fma(c, u, ar); xi[m] = fma(c, v, ai);
+        xr[m + 8] = fma(-c, u, ar); xi[m + 8] = fma(-c, v, ai);
+    }
+    pass16_fwd_tail(xr, xi, w);
+}
 /* inverse pass (x16) */
 IE_HD void pass16_inv(double (&xr)[16], double (&xi)[16], const Tw16 &w)
 {
@@ -194,6 +237,29 @@ IE_HD void pass16_fwd_g(double (&xr)[16], double (&xi)[16], const Tw16g &w)
     bf(xr[12], xi[12], xr[13], xi[13], w.z1bqr, w.z1bqi);
     bf(xr[14], xi[14], xr[15], xi[15], -w.z1bqi, w.z1bqr);
 }
+/* stages 2..4 of pass16_fwd_g */
+IE_HD void pass16_fwd_g_tail(double (&xr)[16], double (&xi)[16], const Tw16g &w)
+{
+#pragma unroll
+    for (int m = 0; m < 4; m++) bf(xr[m], xi[m], xr[m + 4], xi[m + 4], w.z4ar, w.z4ai);
+#pragma unroll
+    for (int m = 8; m < 12; m++) bf(xr[m], xi[m], xr[m + 4], xi[m + 4], w.z4br, w.z4bi);
+#pragma unroll
+    for (int m = 0; m < 2; m++) {
+        bf(xr[m], xi[m], xr[m + 2], xi[m + 2], w.z2ar, w.z2ai);
+        bf(xr[4 + m], xi[4 + m], xr[6 + m], xi[6 + m], -w.z2ai, w.z2ar);
+        bf(xr[8 + m], xi[8 + m], xr[10 + m], xi[10 + m], w.z2br, w.z2bi);
+        bf(xr[12 + m], xi[12 + m], xr[14 + m], xi[14 + m], -w.z2bi, w.z2br);
+    }
+    bf(xr[0], xi[0], xr[1], xi[1], w.z1ar, w.z1ai);
+    bf(xr[2], xi[2], xr[3], xi[3], -w.z1ai, w.z1ar);
+    bf(xr[4], xi[4], xr[5], xi[5], w.z1aqr, w.z1aqi);
+    bf(xr[6], xi[6], xr[7], xi[7], -w.z1aqi, w.z1aqr);
+    bf(xr[8], xi[8], xr[9], xi[9], w.z1br, w.z1bi);
+    bf(xr[10], xi[10], xr[11], xi[11], -w.z1bi, w.z1br);
+    bf(xr[12], xi[12], xr[13], xi[13], w.z1bqr, w.z1bqi);
+    bf(xr[14], xi[14], xr[15], xi[15], -w.z1bqi, w.z1bqr);
+}
 /* uniform final stage: y[s] <- keep + w recv, y[8+s] <- keep - w recv with keep = y[s]; recv is the partner's y[8+s] */
 IE_HD void fin_fwd_apply_folded(double (&yr)[16], double (&yi)[16], const double (&rr)[8], const double (&ri)[8],
                                 const double (&wr)[8], const double (&wi)[8])
@@ -204,6 +270,57 @@ IE_HD void fin_fwd_apply_folded(double (&yr)[16], double (&yi)[16], const double
         bf(yr[s], yi[s], br, bi, wr[s], wi[s]);
         yr[8 + s] = br; yi[8 + s] = bi;
     }
+}
+
+/* ---- select-free inverse of the folded forward transform (persistent 12-warp kernel, br_w12.cu) ----
+ * The folded forward leaves the Lpar = 1 lanes' evaluations multiplied by unit factors: conj(Y) on register s and
+ * -conj(Y) on register 8 + s (Y the butterfly's true twiddle).  Those factors pass through the pointwise product with
+ * the PLAIN key, so the accumulators of an Lpar = 1 lane arrive as u' = conj(Y) u, v' = -conj(Y) v, and with the
+ * twiddle w = conj(Y) the same inverse butterfly every lane runs gives
+ *     x[s] = u' + v' = 2 R_1[8 + s],      x[8 + s] = (u' - v') conj(w) = 2 R_0[8 + s]
+ * where the Lpar = 0 lane gets x[s] = 2 R_0[s], x[8 + s] = 2 R_1[s]: both lanes send registers 8..15 and receive into
+ * them, the Lpar = 1 lane ends with its two halves exchanged, which the inverse of pass16_fwd_g undoes.  No key
+ * factor is left over (Y conj(Y) = 1).
+ * The twiddle table holds w for even s only: w[s + 1] = i w[s] is exact on Lpar = 0 lanes and has the wrong sign on
+ * Lpar = 1 lanes (conj(i Y) = -i conj(Y)); the wrong sign swaps the two outputs of that forward butterfly and the
+ * two inputs of its inverse, i.e. registers s and 8 + s hold each other's evaluation point: a permutation of the
+ * key layout (w12_slot_to_K), nothing else. */
+IE_HD void pass16_inv_g(double (&xr)[16], double (&xi)[16], const Tw16g &w)
+{
+    ibf(xr[0], xi[0], xr[1], xi[1], w.z1ar, w.z1ai);
+    ibf(xr[2], xi[2], xr[3], xi[3], -w.z1ai, w.z1ar);
+    ibf(xr[4], xi[4], xr[5], xi[5], w.z1aqr, w.z1aqi);
+    ibf(xr[6], xi[6], xr[7], xi[7], -w.z1aqi, w.z1aqr);
+    ibf(xr[8], xi[8], xr[9], xi[9], w.z1br, w.z1bi);
+    ibf(xr[10], xi[10], xr[11], xi[11], -w.z1bi, w.z1br);
+    ibf(xr[12], xi[12], xr[13], xi[13], w.z1bqr, w.z1bqi);
+    ibf(xr[14], xi[14], xr[15], xi[15], -w.z1bqi, w.z1bqr);
+#pragma unroll
+    for (int m = 0; m < 2; m++) {
+        ibf(xr[m], xi[m], xr[m + 2], xi[m + 2], w.z2ar, w.z2ai);
+        ibf(xr[4 + m], xi[4 + m], xr[6 + m], xi[6 + m], -w.z2ai, w.z2ar);
+        ibf(xr[8 + m], xi[8 + m], xr[10 + m], xi[10 + m], w.z2br, w.z2bi);
+        ibf(xr[12 + m], xi[12 + m], xr[14 + m], xi[14 + m], -w.z2bi, w.z2br);
+    }
+#pragma unroll
+    for (int m = 0; m < 4; m++) ibf(xr[m], xi[m], xr[m + 4], xi[m + 4], w.z4ar, w.z4ai);
+#pragma unroll
+    for (int m = 8; m < 12; m++) ibf(xr[m], xi[m], xr[m + 4], xi[m + 4], w.z4br, w.z4bi);
+#pragma unroll
+    for (int m = 0; m < 8; m++) ibf(xr[m], xi[m], xr[m + 8], xi[m + 8], w.z8r, w.z8i);
+}
+/* butterflies s = 4 h .. 4 h + 3 of the uniform final stage; za, zb = table entries of s = 4 h and 4 h + 2 */
+IE_HD void fin4_tw(double zar, double zai, double zbr, double zbi, double (&z)[8])
+{
+    z[0] = zar; z[1] = zai; z[2] = -zai; z[3] = zar;
+    z[4] = zbr; z[5] = zbi; z[6] = -zbi; z[7] = zbr;
+}
+/* key slot p of lane l in the layout the 12-warp kernel reads: the plain warp layout with registers s and 8 + s
+ * exchanged for odd s on the Lpar = 1 lanes */
+IE_HD int w12_slot_to_K(int p, int lane)
+{
+    const int q = ((lane >> 4) && (p & 1)) ? (p ^ 8) : p;
+    return brev4(lane & 15) + 16 * brev4((q & 7) + 8 * (lane >> 4)) + 256 * (q >> 3);
 }
 
 /* evaluation index of register p (0..15) of lane l */

@@ -497,7 +497,7 @@ static int run_br(ieache_ctx *ctx, const ieache_cloudkey *key, const GateAddr &g
     const int want_layout = blind_rotate_warp_layout((long long)ga.ntempl * ga.n_inst);
     if (want_layout && key->bkfft_w_kind != want_layout) {
         if (!key->bkfft_w) CU(cudaMalloc((void **)&key->bkfft_w, key->bkfft_bytes));
-        CU(launch_bk_relayout_warp(key->bkfft, key->bkfft_w, (int)(key->bkfft_bytes / (kHalfNBytes)), want_layout == 2, ctx->stream));
+        CU(launch_bk_relayout_warp(key->bkfft, key->bkfft_w, (int)(key->bkfft_bytes / (kHalfNBytes)), want_layout == 1 ? 0 : want_layout, ctx->stream));
         key->bkfft_w_kind = want_layout;
     }
     CU(launch_blind_rotate(key->dp, key->bkfft, want_layout ? key->bkfft_w : nullptr, ga, A, B, ext ? ext : ctx->d_ext, ext_base, ctx->stream));

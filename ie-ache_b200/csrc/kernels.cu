@@ -53,6 +53,8 @@ cudaError_t upload_twiddles()
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbol(d_finf, finf, sizeof(finf));
     if (e != cudaSuccess) return e;
+    e = upload_twiddles_w12();
+    if (e != cudaSuccess) return e;
     return cudaMemcpyToSymbol(d_tw3, tw3, sizeof(tw3));
 }
 
@@ -165,8 +167,14 @@ __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__
 template <int L, int G, int MINB, int ROLL, int NOBK = 0, bool LOCK = false, bool SPREAD = false, bool ACCREG = false>
 __global__ void __launch_bounds__(64 * G, MINB)
 blind_rotate_kernel(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
-                    const int32_t *__restrict__ baseB, int32_t *__restrict__ ext)
+                    const int32_t *__restrict__ baseB, int32_t *__restrict__ ext, int stagger, int sms)
 {
+    /* CTAs that start together run the same program in phase: their FP64 bursts collide and their exchange phases
+     * leave the pipe idle together.  The first wave starts staggered; later CTAs inherit the offsets. */
+    if (stagger > 0 && (int)blockIdx.x < MINB * sms) {
+        const long long wait = (long long)(blockIdx.x / sms) * stagger, t0 = clock64();
+        while (clock64() - t0 < wait) { }
+    }
     blind_rotate_body<L, G, MINB, ROLL, NOBK, LOCK, SPREAD, ACCREG>(p, bkfft, ga, baseA, baseB, ext);
 }
 template <int L, int G, int MINB, int ROLL, int NOBK, bool LOCK, bool SPREAD, bool ACCREG>
@@ -563,10 +571,10 @@ __global__ void __launch_bounds__(512) bk_relayout_warp_kernel(const double2 *__
     const int q = blockIdx.x, idx = threadIdx.x;
     if (q >= npoly) return;
     const int p = idx >> 5, lane = idx & 31;
-    const int K = warp_slot_to_K(p, lane);
+    const int K = folded == 3 ? w12_slot_to_K(p, lane) : warp_slot_to_K(p, lane); /* 3: plain values in the 12-warp kernel's slot order */
     const int t3 = 8 * (K & 7) + ((K >> 3) & 7), r8 = brev3(K >> 6); /* br_core.h: K = b + 8k' + 64 brev3(r), t3 = 8b + k' */
     double2 v = old[(size_t)q * kHalfN + r8 * 64 + t3];
-    if (folded) { /* the unit factor the select-free forward transform leaves on the Lpar = 1 lanes (br_warp.h) */
+    if (folded == 2) { /* the unit factor the select-free forward transform leaves on the Lpar = 1 lanes (br_warp.h) */
         double fr, fi;
         folded_bk_factor(d_finf[lane], p, lane, fr, fi);
         v = make_double2(v.x * fr - v.y * fi, v.x * fi + v.y * fr);
@@ -1192,14 +1200,16 @@ static cudaError_t launch_br_variant(const DevParams &p, const double2 *bkfft, c
     const int grid = (int)((count + G - 1) / G);
     cudaError_t e = cudaFuncSetAttribute(blind_rotate_kernel<L, G, MINB, ROLL, NOBK, LOCK, SPREAD, ACCREG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    blind_rotate_kernel<L, G, MINB, ROLL, NOBK, LOCK, SPREAD, ACCREG><<<grid, 64 * G, smem, s>>>(p, bkfft, ga, baseA, baseB, ext);
+    static const int stagger = [] { const char *e = getenv("IEACHE_BR_STAGGER"); return e ? atoi(e) : 0; }();
+    static const int sms = [] { int d = 0, v = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
+    blind_rotate_kernel<L, G, MINB, ROLL, NOBK, LOCK, SPREAD, ACCREG><<<grid, 64 * G, smem, s>>>(p, bkfft, ga, baseA, baseB, ext, stagger, sms);
     return cudaGetLastError();
 }
 
 int blind_rotate_warp_layout(long long count) /* 0 = not needed, 1 = plain warp layout, 2 = folded (variant 61) */
 {
     if (count <= 0) return 0;
-    return br_variant() == 60 ? 1 : (br_variant() == 61 ? 2 : 0);
+    return br_variant() == 60 ? 1 : (br_variant() == 61 ? 2 : (br_variant() == 70 ? 3 : 0));
 }
 
 cudaError_t launch_blind_rotate(const DevParams &p, const double2 *bkfft, const double2 *bkfft_w, const GateAddr &ga, const int32_t *baseA,
@@ -1227,6 +1237,7 @@ cudaError_t launch_blind_rotate(const DevParams &p, const double2 *bkfft, const 
         if (p.l == 3) return launch_br_pair<3>(p, bkfft, ga, baseA, baseB, ext, count, s);
         if (p.l == 2) return launch_br_pair<2>(p, bkfft, ga, baseA, baseB, ext, count, s);
     }
+    if (bkfft_w && br_variant() == 70) return launch_blind_rotate_w12(p, bkfft_w, ga, baseA, baseB, ext, count, s);
     if (bkfft_w && br_variant() == 60) {
         if (p.l == 3) return launch_br_warp<3, false>(p, bkfft_w, ga, baseA, baseB, ext, count, s);
         if (p.l == 2) return launch_br_warp<2, false>(p, bkfft_w, ga, baseA, baseB, ext, count, s);

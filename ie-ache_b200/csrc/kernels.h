@@ -62,6 +62,10 @@ int blind_rotate_warp_layout(long long count); /* which layout the selected vari
 /* which compiled variant of the throughput blind rotation wide launches use (41 = default register kernel, 60 = one
  * warp per gate with TMEM accumulators, 51/52/55/56 = TMEM accumulators with 64-thread groups, ...); returns the old one */
 int set_throughput_variant(int v);
+/* br_w12.cu: persistent warp-per-gate blind rotation (12 gates per SM), reads the warp-layout key */
+cudaError_t upload_twiddles_w12();
+cudaError_t launch_blind_rotate_w12(const DevParams &p, const double2 *bkfft_w, const GateAddr &ga, const int32_t *baseA,
+                                    const int32_t *baseB, int32_t *ext, long long count, cudaStream_t s);
 cudaError_t launch_bk_relayout_warp(const double2 *bkfft, double2 *bkfft_w, int npoly, int folded, cudaStream_t s);
 /* key switch of ext[g] (+ ext[g + pair_offset] if pair_offset > 0) + (0, cst_post) into sample out of out_base */
 cudaError_t launch_keyswitch(const DevParams &p, const int32_t *ksk, const GateAddr &ga, int32_t *out_base,

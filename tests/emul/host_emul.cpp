@@ -280,6 +280,97 @@ void emul_warp_blind_rotate(int n, int l, int Bgbit, int32_t mu, const int32_t *
 
 } // extern "C"
 
+/* ------------------------------------------------------------------ persistent 12-warp kernel (br_w12.cu)
+ * Same layout as the warp kernel; differs in pass 1 (straight from the integer digits, pass16_fwd_from_digits) and in
+ * the final-stage twiddle table (4 complex per lane, z[s + 1] = i z[s] for even s). */
+extern "C" {
+void emul_w12_blind_rotate(int n, int l, int Bgbit, int32_t mu, const int32_t *bk_coef, const int32_t *x, int32_t *ext)
+{
+    const EmulW &e = emulw();
+    const int kpl = 2 * l;
+    std::vector<double> bkw((size_t)n * kpl * 2 * 1024);
+    {
+        int pos_of_K[512];
+        for (int r = 0; r < 8; r++) for (int t3 = 0; t3 < 64; t3++) pos_of_K[emul_slot_to_K(r, t3)] = r * 64 + t3;
+        std::vector<double> old(1024);
+        for (long q = 0; q < (long)n * kpl * 2; q++) {
+            emul_poly_fft(bk_coef + (size_t)q * kN, old.data(), 1.0 / 512.0);
+            double *dst = &bkw[(size_t)q * 1024];
+            for (int p = 0; p < 16; p++) for (int lane = 0; lane < 32; lane++) {
+                const int src = pos_of_K[warp_slot_to_K(p, lane)];
+                dst[2 * (p * 32 + lane)] = old[2 * src]; dst[2 * (p * 32 + lane) + 1] = old[2 * src + 1];
+            }
+        }
+    }
+    /* the kernel's 4-entry table and the full one it stands for */
+    FinTw fin4[32];
+    for (int lane = 0; lane < 32; lane++)
+        for (int h = 0; h < 4; h++) {
+            fin4[lane].zr[2 * h] = e.fin[lane].zr[2 * h]; fin4[lane].zi[2 * h] = e.fin[lane].zi[2 * h];
+            fin4[lane].zr[2 * h + 1] = -e.fin[lane].zi[2 * h]; fin4[lane].zi[2 * h + 1] = e.fin[lane].zr[2 * h];
+        }
+    std::vector<int32_t> acc(2 * kN);
+    std::vector<int> abar(n + 1);
+    for (int i = 0; i <= n; i++) abar[i] = modswitch_2N(x[i]);
+    {
+        const int a = (2 * kN - abar[n]) & (2 * kN - 1), ar = a & (kN - 1);
+        const bool flip = a >= kN;
+        for (int j = 0; j < kN; j++) { acc[j] = 0; acc[kN + j] = ((j < ar) != flip) ? -mu : mu; }
+    }
+    const uint32_t maskBg = (1u << Bgbit) - 1;
+    const int32_t halfBg = 1 << (Bgbit - 1);
+    uint32_t offset = 0;
+    for (int i = 1; i <= l; i++) offset += (uint32_t)halfBg << (32 - i * Bgbit);
+    Regs16 t[32];
+    cd buf[kWarpBufElems];
+    std::vector<double> sr(32 * 2 * 16), si(32 * 2 * 16);
+    for (int i = 0; i < n; i++) {
+        const int a = abar[i];
+        if (a == 0) continue;
+        std::fill(sr.begin(), sr.end(), 0.0); std::fill(si.begin(), si.end(), 0.0);
+        for (int q = 0; q < 2; q++) {
+            uint32_t cc[32][32];
+            for (int lane = 0; lane < 32; lane++) {
+                int32_t c[32];
+                rot_minus_one32(&acc[q * kN], lane, a, c);
+                for (int h = 0; h < 32; h++) cc[lane][h] = (uint32_t)c[h] + offset;
+            }
+            for (int pp = 0; pp < l; pp++) {
+                const int shift = 32 - (pp + 1) * Bgbit;
+                for (int lane = 0; lane < 32; lane++) { pass16_fwd_from_digits(cc[lane], shift, maskBg, halfBg, t[lane].xr, t[lane].xi, e.w1); st16_pass1(buf, lane, t[lane].xr, t[lane].xi); }
+                for (int lane = 0; lane < 32; lane++) { ld16_pass2(buf, lane, t[lane].xr, t[lane].xi); pass16_fwd(t[lane].xr, t[lane].xi, e.w2[lane & 15]); }
+                double ssr[32][8], ssi[32][8];
+                for (int lane = 0; lane < 32; lane++) fin_fwd_send(t[lane].xr, t[lane].xi, lane >> 4, ssr[lane], ssi[lane]);
+                for (int lane = 0; lane < 32; lane++) fin_fwd_apply(t[lane].xr, t[lane].xi, lane >> 4, ssr[lane ^ 16], ssi[lane ^ 16], fin4[lane].zr, fin4[lane].zi);
+                const double *bk_r = &bkw[(((size_t)i * kpl + q * l + pp) * 2) * 1024];
+                for (int lane = 0; lane < 32; lane++)
+                    for (int j = 0; j < 2; j++)
+                        for (int p = 0; p < 16; p++) {
+                            const double *b = bk_r + (size_t)j * 1024 + 2 * (p * 32 + lane);
+                            cmac(sr[(lane * 2 + j) * 16 + p], si[(lane * 2 + j) * 16 + p], t[lane].xr[p], t[lane].xi[p], b[0], b[1]);
+                        }
+            }
+        }
+        for (int j = 0; j < 2; j++) {
+            for (int lane = 0; lane < 32; lane++)
+                for (int p = 0; p < 16; p++) { t[lane].xr[p] = sr[(lane * 2 + j) * 16 + p]; t[lane].xi[p] = si[(lane * 2 + j) * 16 + p]; }
+            double ssr[32][8], ssi[32][8];
+            for (int lane = 0; lane < 32; lane++) { fin_inv_local(t[lane].xr, t[lane].xi, fin4[lane].zr, fin4[lane].zi); fin_inv_send(t[lane].xr, t[lane].xi, lane >> 4, ssr[lane], ssi[lane]); }
+            for (int lane = 0; lane < 32; lane++) fin_inv_place(t[lane].xr, t[lane].xi, lane >> 4, ssr[lane ^ 16], ssi[lane ^ 16]);
+            for (int lane = 0; lane < 32; lane++) { pass16_inv(t[lane].xr, t[lane].xi, e.w2[lane & 15]); st16_ipass2(buf, lane, t[lane].xr, t[lane].xi); }
+            for (int lane = 0; lane < 32; lane++) { ld16_ipass1(buf, lane, t[lane].xr, t[lane].xi); pass16_inv(t[lane].xr, t[lane].xi, e.w1); }
+            for (int lane = 0; lane < 32; lane++)
+                for (int m = 0; m < 16; m++) {
+                    acc[j * kN + lane + 32 * m] += round_to_torus(t[lane].xr[m]);
+                    acc[j * kN + lane + 32 * m + 512] += round_to_torus(t[lane].xi[m]);
+                }
+        }
+    }
+    for (int j = 0; j < kN; j++) ext[j] = (j == 0) ? acc[0] : -acc[kN - j];
+    ext[kN] = acc[kN];
+}
+} // extern "C"
+
 /* ------------------------------------------------------------------ folded forward variant of the warp layout */
 namespace {
 struct EmulWF {
@@ -316,5 +407,112 @@ void emul_warpf_fft_unfolded(const int32_t *coef, double *out /*512*2*/)
             out[2 * (p * 32 + l)] = t[l].xr[p] * fr - t[l].xi[p] * fi;
             out[2 * (p * 32 + l) + 1] = t[l].xr[p] * fi + t[l].xi[p] * fr;
         }
+}
+} // extern "C"
+
+/* ------------------------------------------------------------------ 12-warp kernel, select-free form (br_w12.cu)
+ * folded forward AND folded inverse, 4-entry final-stage table with the uniform rule w[s + 1] = i w[s], plain key
+ * values in the w12_slot_to_K order */
+extern "C" {
+int emul_w12_slot_to_K(int p, int lane) { return w12_slot_to_K(p, lane); }
+void emul_w12f_blind_rotate(int n, int l, int Bgbit, int32_t mu, const int32_t *bk_coef, const int32_t *x, int32_t *ext)
+{
+    const EmulWF &e = emulwf();
+    const int kpl = 2 * l;
+    std::vector<double> bkw((size_t)n * kpl * 2 * 1024);
+    {
+        int pos_of_K[512];
+        for (int r = 0; r < 8; r++) for (int t3 = 0; t3 < 64; t3++) pos_of_K[emul_slot_to_K(r, t3)] = r * 64 + t3;
+        std::vector<double> old(1024);
+        for (long q = 0; q < (long)n * kpl * 2; q++) {
+            emul_poly_fft(bk_coef + (size_t)q * kN, old.data(), 1.0 / 512.0);
+            double *dst = &bkw[(size_t)q * 1024];
+            for (int p = 0; p < 16; p++) for (int lane = 0; lane < 32; lane++) {
+                const int src = pos_of_K[w12_slot_to_K(p, lane)];
+                dst[2 * (p * 32 + lane)] = old[2 * src]; dst[2 * (p * 32 + lane) + 1] = old[2 * src + 1];
+            }
+        }
+    }
+    std::vector<int32_t> acc(2 * kN);
+    std::vector<int> abar(n + 1);
+    for (int i = 0; i <= n; i++) abar[i] = modswitch_2N(x[i]);
+    {
+        const int a = (2 * kN - abar[n]) & (2 * kN - 1), ar = a & (kN - 1);
+        const bool flip = a >= kN;
+        for (int j = 0; j < kN; j++) { acc[j] = 0; acc[kN + j] = ((j < ar) != flip) ? -mu : mu; }
+    }
+    const uint32_t maskBg = (1u << Bgbit) - 1;
+    const int32_t halfBg = 1 << (Bgbit - 1);
+    uint32_t offset = 0;
+    for (int i = 1; i <= l; i++) offset += (uint32_t)halfBg << (32 - i * Bgbit);
+    Regs16 t[32];
+    cd buf[kWarpBufElems];
+    std::vector<double> sr(32 * 2 * 16), si(32 * 2 * 16);
+    auto fin_z = [&](int lane, int h, double (&z)[8]) {
+        fin4_tw(e.fin[lane].zr[4 * h], e.fin[lane].zi[4 * h], e.fin[lane].zr[4 * h + 2], e.fin[lane].zi[4 * h + 2], z);
+    };
+    for (int i = 0; i < n; i++) {
+        const int a = abar[i];
+        if (a == 0) continue;
+        std::fill(sr.begin(), sr.end(), 0.0); std::fill(si.begin(), si.end(), 0.0);
+        for (int q = 0; q < 2; q++) {
+            uint32_t cc[32][32];
+            for (int lane = 0; lane < 32; lane++) {
+                int32_t c[32];
+                rot_minus_one32(&acc[q * kN], lane, a, c);
+                for (int h = 0; h < 32; h++) cc[lane][h] = (uint32_t)c[h] + offset;
+            }
+            for (int pp = 0; pp < l; pp++) {
+                const int shift = 32 - (pp + 1) * Bgbit;
+                for (int lane = 0; lane < 32; lane++) { pass16_fwd_from_digits(cc[lane], shift, maskBg, halfBg, t[lane].xr, t[lane].xi, e.w1); st16_pass1(buf, lane, t[lane].xr, t[lane].xi); }
+                for (int lane = 0; lane < 32; lane++) { ld16_pass2(buf, lane, t[lane].xr, t[lane].xi); pass16_fwd_g(t[lane].xr, t[lane].xi, e.w2[lane]); }
+                double ssr[32][8], ssi[32][8];
+                for (int lane = 0; lane < 32; lane++) for (int s8 = 0; s8 < 8; s8++) { ssr[lane][s8] = t[lane].xr[8 + s8]; ssi[lane][s8] = t[lane].xi[8 + s8]; }
+                for (int lane = 0; lane < 32; lane++)
+                    for (int h = 0; h < 2; h++) {
+                        double z[8];
+                        fin_z(lane, h, z);
+                        for (int s4 = 0; s4 < 4; s4++) {
+                            const int k = 4 * h + s4;
+                            double br = ssr[lane ^ 16][k], bi = ssi[lane ^ 16][k];
+                            bf(t[lane].xr[k], t[lane].xi[k], br, bi, z[2 * s4], z[2 * s4 + 1]);
+                            t[lane].xr[8 + k] = br; t[lane].xi[8 + k] = bi;
+                        }
+                    }
+                const double *bk_r = &bkw[(((size_t)i * kpl + q * l + pp) * 2) * 1024];
+                for (int lane = 0; lane < 32; lane++)
+                    for (int j = 0; j < 2; j++)
+                        for (int p = 0; p < 16; p++) {
+                            const double *b = bk_r + (size_t)j * 1024 + 2 * (p * 32 + lane);
+                            cmac(sr[(lane * 2 + j) * 16 + p], si[(lane * 2 + j) * 16 + p], t[lane].xr[p], t[lane].xi[p], b[0], b[1]);
+                        }
+            }
+        }
+        for (int j = 0; j < 2; j++) {
+            for (int lane = 0; lane < 32; lane++)
+                for (int p = 0; p < 16; p++) { t[lane].xr[p] = sr[(lane * 2 + j) * 16 + p]; t[lane].xi[p] = si[(lane * 2 + j) * 16 + p]; }
+            double ssr[32][8], ssi[32][8];
+            for (int lane = 0; lane < 32; lane++)
+                for (int h = 0; h < 2; h++) {
+                    double z[8];
+                    fin_z(lane, h, z);
+                    for (int s4 = 0; s4 < 4; s4++) {
+                        const int k = 4 * h + s4;
+                        ibf(t[lane].xr[k], t[lane].xi[k], t[lane].xr[8 + k], t[lane].xi[8 + k], z[2 * s4], z[2 * s4 + 1]);
+                        ssr[lane][k] = t[lane].xr[8 + k]; ssi[lane][k] = t[lane].xi[8 + k];
+                    }
+                }
+            for (int lane = 0; lane < 32; lane++) for (int s8 = 0; s8 < 8; s8++) { t[lane].xr[8 + s8] = ssr[lane ^ 16][s8]; t[lane].xi[8 + s8] = ssi[lane ^ 16][s8]; }
+            for (int lane = 0; lane < 32; lane++) { pass16_inv_g(t[lane].xr, t[lane].xi, e.w2[lane]); st16_ipass2(buf, lane, t[lane].xr, t[lane].xi); }
+            for (int lane = 0; lane < 32; lane++) { ld16_ipass1(buf, lane, t[lane].xr, t[lane].xi); pass16_inv(t[lane].xr, t[lane].xi, e.w1); }
+            for (int lane = 0; lane < 32; lane++)
+                for (int m = 0; m < 16; m++) {
+                    acc[j * kN + lane + 32 * m] += round_to_torus(t[lane].xr[m]);
+                    acc[j * kN + lane + 32 * m + 512] += round_to_torus(t[lane].xi[m]);
+                }
+        }
+    }
+    for (int j = 0; j < kN; j++) ext[j] = (j == 0) ? acc[0] : -acc[kN - j];
+    ext[kN] = acc[kN];
 }
 } // extern "C"

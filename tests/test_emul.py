@@ -143,6 +143,57 @@ def test_warp_blind_rotate_matches_oracle(emul, oracle, n, l, bgbit):
     ks.free()
 
 
+@pytest.mark.parametrize("n,l,bgbit", [(24, 3, 7), (12, 2, 10)])
+def test_w12_blind_rotate_matches_oracle(emul, oracle, n, l, bgbit):
+    """the persistent 12-warp kernel's arithmetic (br_w12.cu): pass 1 from the integer digits, 4-entry final-stage table"""
+    p = ob.params_default(n)
+    p.bk_l, p.bk_Bgbit = l, bgbit
+    ks = oracle.keygen(p, seed=779)
+    bits = np.array([1, 0, 1, 1, 0, 0], dtype=np.int32)
+    s = ks.encrypt(bits, 7)
+    mu = 1 << 29
+    bk = ks.bk_coef()
+    for g in range(6):
+        x = (s[g] + s[(g + 1) % 6]).astype(np.int32)
+        x[n] = np.int32((int(x[n]) - mu + 2 ** 31) % 2 ** 32 - 2 ** 31)
+        ext_o = ks.bootstrap_woks(x[None])[0]
+        ext_e = np.zeros(1025, dtype=np.int32)
+        emul.emul_w12_blind_rotate(n, l, bgbit, ctypes.c_int32(mu), vp(bk), vp(x), vp(ext_e))
+        ph = ks.phase_extracted(ext_e[None])[0]
+        assert (ph > 0) == bool(bits[g] & bits[(g + 1) % 6])
+        d = ext_o.astype(np.int64) - ext_e.astype(np.int64)
+        d = ((d + 2 ** 31) % 2 ** 32) - 2 ** 31
+        assert np.abs(d).max() <= 2
+    ks.free()
+
+
+@pytest.mark.parametrize("n,l,bgbit", [(24, 3, 7), (12, 2, 10)])
+def test_w12_select_free_blind_rotate_matches_oracle(emul, oracle, n, l, bgbit):
+    """br_w12.cu as shipped: folded forward and folded inverse (no lane-dependent selects), uniform rule for the odd
+    final-stage twiddles, plain key values permuted by w12_slot_to_K"""
+    emul.emul_w12_slot_to_K.restype = ctypes.c_int
+    assert sorted(emul.emul_w12_slot_to_K(p, ln) for p in range(16) for ln in range(32)) == list(range(512))
+    p = ob.params_default(n)
+    p.bk_l, p.bk_Bgbit = l, bgbit
+    ks = oracle.keygen(p, seed=780)
+    bits = np.array([1, 0, 1, 1, 0, 0], dtype=np.int32)
+    s = ks.encrypt(bits, 8)
+    mu = 1 << 29
+    bk = ks.bk_coef()
+    for g in range(6):
+        x = (s[g] + s[(g + 1) % 6]).astype(np.int32)
+        x[n] = np.int32((int(x[n]) - mu + 2 ** 31) % 2 ** 32 - 2 ** 31)
+        ext_o = ks.bootstrap_woks(x[None])[0]
+        ext_e = np.zeros(1025, dtype=np.int32)
+        emul.emul_w12f_blind_rotate(n, l, bgbit, ctypes.c_int32(mu), vp(bk), vp(x), vp(ext_e))
+        ph = ks.phase_extracted(ext_e[None])[0]
+        assert (ph > 0) == bool(bits[g] & bits[(g + 1) % 6])
+        d = ext_o.astype(np.int64) - ext_e.astype(np.int64)
+        d = ((d + 2 ** 31) % 2 ** 32) - 2 ** 31
+        assert np.abs(d).max() <= 2
+    ks.free()
+
+
 def test_warp_folded_forward_equals_plain_after_key_factor(emul):
     """the select-free forward variant leaves the Lpar = 1 lanes' results scaled by unit factors that the key layout
     carries: multiplied back, it must reproduce the plain warp-layout spectrum"""

@@ -52,15 +52,15 @@ def small(pkg, oracle, eng):
     key.close(); ks.free(); nbit.free()
 
 
-@pytest.fixture(params=["cluster_kernel", "pair_kernel", "throughput_kernel", "warp_tmem_kernel", "warp_tmem_folded_kernel", "group_tmem_kernel"])
+@pytest.fixture(params=["cluster_kernel", "pair_kernel", "throughput_kernel", "w12_kernel", "warp_tmem_kernel", "warp_tmem_folded_kernel", "group_tmem_kernel"])
 def kernel_mode(pkg, request):
     """every blind-rotation kernel (one gate on a 2-SM cluster / on two groups of one SM / one group per gate with
     the accumulators in registers / one warp per gate with the accumulators in tensor memory / one group serving two
     gates with TMEM accumulators) must pass the same parity tests whatever the launch size"""
-    throughput = request.param in ("throughput_kernel", "warp_tmem_kernel", "warp_tmem_folded_kernel", "group_tmem_kernel")
+    throughput = request.param in ("throughput_kernel", "w12_kernel", "warp_tmem_kernel", "warp_tmem_folded_kernel", "group_tmem_kernel")
     old = pkg.set_wide_max(0 if throughput else 1 << 40)
     oldc = pkg.set_cluster_max(1 << 40 if request.param == "cluster_kernel" else 0)
-    oldv = pkg.set_throughput_variant({"warp_tmem_kernel": 60, "warp_tmem_folded_kernel": 61, "group_tmem_kernel": 52}.get(request.param, 41))
+    oldv = pkg.set_throughput_variant({"w12_kernel": 70, "warp_tmem_kernel": 60, "warp_tmem_folded_kernel": 61, "group_tmem_kernel": 52}.get(request.param, 41))
     yield request.param
     pkg.set_wide_max(old)
     pkg.set_cluster_max(oldc)
