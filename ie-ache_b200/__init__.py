@@ -94,12 +94,9 @@ def lib() -> ctypes.CDLL:
     L.ieache_circuit_eval.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]
     L.ieache_circuit_eval_device.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]
     L.ieache_cloud_run.argtypes = [c_void_p, c_char_p, POINTER(c_double)]
-    L.ieache_set_wide_max.restype = ctypes.c_int64
-    L.ieache_set_wide_max.argtypes = [ctypes.c_int64]
-    L.ieache_set_cluster_max.restype = ctypes.c_int64
-    L.ieache_set_cluster_max.argtypes = [ctypes.c_int64]
-    L.ieache_set_ks_staged_min.restype = ctypes.c_int64
-    L.ieache_set_ks_staged_min.argtypes = [ctypes.c_int64]
+    L.ieache_ctx_set_tuning.argtypes = [c_void_p, c_int, ctypes.c_int64, POINTER(ctypes.c_int64)]
+    L.ieache_ctx_pick_kernels.argtypes = [c_void_p, c_void_p, ctypes.c_int64, POINTER(c_int), POINTER(c_int)]
+    L.ieache_ctx_copy_counts.argtypes = [c_void_p, POINTER(c_uint64), POINTER(c_uint64)]
     L.ieache_ctx_timer_start.argtypes = [c_void_p]
     L.ieache_ctx_timer_stop.argtypes = [c_void_p, POINTER(c_double)]
     L.ieache_measure_fp64_peak.argtypes = [c_void_p, POINTER(c_double)]
@@ -146,24 +143,9 @@ def verif_run(directory: str):
     return int(buf.value.decode()), sc.value, w.value
 
 
-def set_wide_max(max_gates: int) -> int:
-    """Launches of <= max_gates gates use the latency kernel; returns the previous threshold."""
-    return lib().ieache_set_wide_max(max_gates)
-
-
-def set_throughput_variant(variant: int) -> int:
-    """Which compiled variant of the throughput blind rotation is used (41 default, 60 warp-per-gate/TMEM); returns the old one."""
-    return lib().ieache_set_throughput_variant(variant)
-
-
-def set_ks_staged_min(min_gates: int) -> int:
-    """Key-switch launches of >= min_gates gates use the staged kernel; returns the previous threshold."""
-    return lib().ieache_set_ks_staged_min(min_gates)
-
-
-def set_cluster_max(max_gates: int) -> int:
-    """Launches of <= max_gates gates use the 2-SM cluster latency kernel; returns the previous threshold."""
-    return lib().ieache_set_cluster_max(max_gates)
+TUNE_CLUSTER_MAX, TUNE_PAIR_MAX, TUNE_W12_MIN, TUNE_KS_STAGED_MIN, TUNE_THROUGHPUT_KERNEL = 1, 2, 3, 4, 5
+KERNEL_CLUSTER, KERNEL_PAIR, KERNEL_GROUP, KERNEL_W12 = 1, 2, 41, 70
+KS_CLUSTER, KS_GATHER, KS_STAGED = 1, 2, 3
 
 
 def _check(rc: int) -> None:
@@ -320,12 +302,47 @@ class Session:
 
 
 class Engine:
-    """One engine context per process and GPU."""
+    """One engine context per GPU (a process may hold several: the launch policy lives in the context)."""
 
     def __init__(self, device: int = 0):
         self._h = c_void_p()
         _check(lib().ieache_ctx_create(device, byref(self._h)))
         self.device = device
+
+    # ---- launch policy (which kernel shape a launch of a given size uses) --------------------
+    def set_tuning(self, which: int, value: int) -> int:
+        """ieache_ctx_set_tuning: returns the previous value; raises EngineError for a value the library refuses."""
+        old = ctypes.c_int64()
+        _check(lib().ieache_ctx_set_tuning(self._h, which, value, byref(old)))
+        return old.value
+
+    def set_cluster_max(self, max_gates: int) -> int:
+        return self.set_tuning(TUNE_CLUSTER_MAX, max_gates)
+
+    def set_pair_max(self, max_gates: int) -> int:
+        return self.set_tuning(TUNE_PAIR_MAX, max_gates)
+
+    def set_w12_min(self, min_gates: int) -> int:
+        return self.set_tuning(TUNE_W12_MIN, min_gates)
+
+    def set_ks_staged_min(self, min_gates: int) -> int:
+        return self.set_tuning(TUNE_KS_STAGED_MIN, min_gates)
+
+    def set_throughput_kernel(self, kernel: int) -> int:
+        """0 = by size, KERNEL_GROUP or KERNEL_W12 for every launch above the two-group threshold"""
+        return self.set_tuning(TUNE_THROUGHPUT_KERNEL, kernel)
+
+    def pick_kernels(self, key: "CloudKey", count: int):
+        """(blind-rotation kernel, key-switch kernel) a launch of `count` gates would use"""
+        br, ks = c_int(), c_int()
+        _check(lib().ieache_ctx_pick_kernels(self._h, key._h, count, byref(br), byref(ks)))
+        return br.value, ks.value
+
+    def copy_counts(self):
+        """(host->device, device->host) 352-sample blocks moved by the session calls so far"""
+        a, b = c_uint64(), c_uint64()
+        _check(lib().ieache_ctx_copy_counts(self._h, byref(a), byref(b)))
+        return a.value, b.value
 
     def close(self):
         if self._h:
@@ -427,8 +444,9 @@ class Engine:
     def eval_device(self, key: CloudKey, circ: Circuit, in_dev: int, out_dev: int, n_expr: int):
         _check(lib().ieache_circuit_eval_device(self._h, key._h, circ._h, c_void_p(in_dev), c_void_p(out_dev), n_expr))
 
-    def keygen_files(self, directory: str, params: Params | None = None, seed_key: int = 314_1592_657, seed_nbit: int = 314_1592_888):
-        """Keygen/keygen.c: secret.key, cloud.key, nbit.key (the default seeds echo the reference's seed triples)"""
+    def keygen_files(self, directory: str, params: Params | None = None, seed_key: int = 0, seed_nbit: int = 0):
+        """Keygen/keygen.c: secret.key, cloud.key, nbit.key.  Seeds 0 (default) = operating-system entropy; a non-zero
+        seed gives a reproducible key set for tests only (the key set is then no more secret than the seed)"""
         _check(lib().ieache_keygen_files(self._h, directory.encode(), byref(params) if params is not None else None, seed_key, seed_nbit))
 
     def session(self, cloud_key_path: str, nbit_key_path: str) -> Session:

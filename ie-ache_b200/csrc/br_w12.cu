@@ -26,15 +26,6 @@
 
 #include <stdlib.h>
 
-#ifndef W12_BOUNDS
-#define W12_BOUNDS __launch_bounds__(32 * kW12Warps, 1)
-#endif
-#ifndef W12_FUSED_LD
-#define W12_FUSED_LD 1
-#endif
-#ifndef W12_PREFETCH
-#define W12_PREFETCH 1
-#endif
 
 namespace ieache {
 
@@ -67,15 +58,6 @@ __device__ __forceinline__ uint32_t smem_u32_w12(const void *p) { return (uint32
 
 /* 16 columns = 8 doubles, 32 columns = 16 doubles of the calling lane.  The b32 halves are packed inside the asm so
  * that ptxas allocates them as the register pairs of the doubles. */
-#define W12_LD8D(taddr, d) asm volatile("{\n\t.reg .b32 t<16>;\n\t" \
-    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {t0,t1,t2,t3,t4,t5,t6,t7,t8,t9,t10,t11,t12,t13,t14,t15}, [%8];\n\t" \
-    "tcgen05.wait::ld.sync.aligned;\n\t" \
-    "mov.b64 %0, {t0,t1};\n\tmov.b64 %1, {t2,t3};\n\tmov.b64 %2, {t4,t5};\n\tmov.b64 %3, {t6,t7};\n\tmov.b64 %4, {t8,t9};\n\tmov.b64 %5, {t10,t11};\n\tmov.b64 %6, {t12,t13};\n\tmov.b64 %7, {t14,t15};\n\t}" \
-    : "=d"(d[0]),"=d"(d[1]),"=d"(d[2]),"=d"(d[3]),"=d"(d[4]),"=d"(d[5]),"=d"(d[6]),"=d"(d[7]) : "r"(taddr) : "memory")
-#define W12_ST8D(taddr, d) asm volatile("{\n\t.reg .b32 t<16>;\n\t" \
-    "mov.b64 {t0,t1}, %1;\n\tmov.b64 {t2,t3}, %2;\n\tmov.b64 {t4,t5}, %3;\n\tmov.b64 {t6,t7}, %4;\n\tmov.b64 {t8,t9}, %5;\n\tmov.b64 {t10,t11}, %6;\n\tmov.b64 {t12,t13}, %7;\n\tmov.b64 {t14,t15}, %8;\n\t" \
-    "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {t0,t1,t2,t3,t4,t5,t6,t7,t8,t9,t10,t11,t12,t13,t14,t15};\n\t}" \
-    :: "r"(taddr), "d"(d[0]),"d"(d[1]),"d"(d[2]),"d"(d[3]),"d"(d[4]),"d"(d[5]),"d"(d[6]),"d"(d[7]) : "memory")
 #define W12_LD16D(taddr, d) asm volatile("{\n\t.reg .b32 t<32>;\n\t" \
     "tcgen05.ld.sync.aligned.32x32b.x32.b32 {t0,t1,t2,t3,t4,t5,t6,t7,t8,t9,t10,t11,t12,t13,t14,t15,t16,t17,t18,t19,t20,t21,t22,t23,t24,t25,t26,t27,t28,t29,t30,t31}, [%16];\n\t" \
     "tcgen05.wait::ld.sync.aligned;\n\t" \
@@ -96,24 +78,6 @@ __device__ __forceinline__ uint32_t smem_u32_w12(const void *p) { return (uint32
 /* 16 columns of zeros */
 #define W12_ST_ZERO16(taddr) asm volatile("{\n\t.reg .b32 z;\n\tmov.b32 z, 0;\n\t" \
     "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {z,z,z,z,z,z,z,z,z,z,z,z,z,z,z,z};\n\t}" :: "r"(taddr) : "memory")
-
-/* One multiply-accumulate chunk as a single block: 16 accumulator columns (4 slots x {re, im}) come from TMEM, take
- * acc += x * b for the 4 slots and go back.  Written as one asm statement so that the load and the store name the
- * same 16 registers and the FMAs run in place: as separate statements ptxas gave the load and the store different
- * register blocks and paid 12-16 moves per chunk (each holds the dispatch port for two cycles, like a DFMA). */
-#define W12_MAC4(taddr, x0r, x0i, x1r, x1i, x2r, x2i, x3r, x3i, b0, b1, b2, b3) asm volatile("{\n\t.reg .b32 t<16>;\n\t.reg .f64 a<8>;\n\t.reg .f64 n<4>;\n\t" \
-    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {t0,t1,t2,t3,t4,t5,t6,t7,t8,t9,t10,t11,t12,t13,t14,t15}, [%0];\n\t" \
-    "neg.f64 n0, %2;\n\tneg.f64 n1, %4;\n\tneg.f64 n2, %6;\n\tneg.f64 n3, %8;\n\t" \
-    "tcgen05.wait::ld.sync.aligned;\n\t" \
-    "mov.b64 a0, {t0,t1};\n\tmov.b64 a1, {t2,t3};\n\tmov.b64 a2, {t4,t5};\n\tmov.b64 a3, {t6,t7};\n\tmov.b64 a4, {t8,t9};\n\tmov.b64 a5, {t10,t11};\n\tmov.b64 a6, {t12,t13};\n\tmov.b64 a7, {t14,t15};\n\t" \
-    "fma.rn.f64 a0, %1, %9, a0;\n\tfma.rn.f64 a1, %1, %10, a1;\n\tfma.rn.f64 a2, %3, %11, a2;\n\tfma.rn.f64 a3, %3, %12, a3;\n\t" \
-    "fma.rn.f64 a4, %5, %13, a4;\n\tfma.rn.f64 a5, %5, %14, a5;\n\tfma.rn.f64 a6, %7, %15, a6;\n\tfma.rn.f64 a7, %7, %16, a7;\n\t" \
-    "fma.rn.f64 a0, n0, %10, a0;\n\tfma.rn.f64 a1, %2, %9, a1;\n\tfma.rn.f64 a2, n1, %12, a2;\n\tfma.rn.f64 a3, %4, %11, a3;\n\t" \
-    "fma.rn.f64 a4, n2, %14, a4;\n\tfma.rn.f64 a5, %6, %13, a5;\n\tfma.rn.f64 a6, n3, %16, a6;\n\tfma.rn.f64 a7, %8, %15, a7;\n\t" \
-    "mov.b64 {t0,t1}, a0;\n\tmov.b64 {t2,t3}, a1;\n\tmov.b64 {t4,t5}, a2;\n\tmov.b64 {t6,t7}, a3;\n\tmov.b64 {t8,t9}, a4;\n\tmov.b64 {t10,t11}, a5;\n\tmov.b64 {t12,t13}, a6;\n\tmov.b64 {t14,t15}, a7;\n\t" \
-    "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {t0,t1,t2,t3,t4,t5,t6,t7,t8,t9,t10,t11,t12,t13,t14,t15};\n\t}" \
-    :: "r"(taddr), "d"(x0r), "d"(x0i), "d"(x1r), "d"(x1i), "d"(x2r), "d"(x2i), "d"(x3r), "d"(x3i), \
-       "d"((b0).x), "d"((b0).y), "d"((b1).x), "d"((b1).y), "d"((b2).x), "d"((b2).y), "d"((b3).x), "d"((b3).y) : "memory")
 
 /* 4 slots (16 columns) as four 4-register accesses: a slot's {re, im} is one aligned register quad, the same
  * constraint ptxas already solves for 16-byte shared-memory accesses, so the accumulate needs no register moves
@@ -197,9 +161,9 @@ __device__ __forceinline__ void w12_load_tw2(Tw16g &w, uint32_t t_tw2, const dou
 }
 
 template <int L>
-__global__ void W12_BOUNDS
+__global__ void __launch_bounds__(32 * kW12Warps, 1)
 blind_rotate_w12_kernel(DevParams p, const double2 *__restrict__ bkw, GateAddr ga, const int32_t *__restrict__ baseA,
-                        const int32_t *__restrict__ baseB, int32_t *__restrict__ ext, int stagger)
+                        const int32_t *__restrict__ baseB, int32_t *__restrict__ ext)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t tmem_base_slot;
@@ -251,13 +215,6 @@ blind_rotate_w12_kernel(DevParams p, const double2 *__restrict__ bkw, GateAddr g
     const long long total = (long long)ga.ntempl * ga.n_inst;
     const long long slots = (long long)gridDim.x * kW12Warps;
 
-    /* Every warp runs the same program on the same number of steps, so warps that start together stay in phase: their
-     * FP64 bursts collide on the pipe and their exchange / rotation phases leave it idle together.  A start offset
-     * per warp persists (nothing pulls the warps back into phase) and spreads the phases over the step. */
-    if (stagger > 0) {
-        const long long wait = (long long)(4 * (warp >> 2) + (warp & 3)) * stagger, t0 = clock64();
-        while (clock64() - t0 < wait) { }
-    }
     for (long long g = blockIdx.x + (long long)gridDim.x * warp; g < total; g += slots) {
         /* 1. linear pre-combination + modSwitch to Z_{2N} */
         {
@@ -323,20 +280,8 @@ blind_rotate_w12_kernel(DevParams p, const double2 *__restrict__ bkw, GateAddr g
                     {
                         Tw16g w2;
                         w12_load_tw2(w2, t_tw2, s_tab, lane);
-#if W12_FUSED_LD
-                        /* loads in the order the first stage consumes them (m, m + 8): short live ranges for the loaded quads */
-                        const cd *src = buf + (lane & 15) * 33 + (lane >> 4);
-#pragma unroll
-                        for (int m = 0; m < 8; m++) {
-                            const cd a = src[2 * m], b = src[2 * (m + 8)];
-                            xr[m] = a.x; xi[m] = a.y; xr[m + 8] = b.x; xi[m + 8] = b.y;
-                            bf(xr[m], xi[m], xr[m + 8], xi[m + 8], w2.z8r, w2.z8i);
-                        }
-                        pass16_fwd_g_tail(xr, xi, w2);
-#else
                         ld16_pass2(buf, lane, xr, xi);
                         pass16_fwd_g(xr, xi, w2);
-#endif
                     }
                     w12_fin_fwd_half<0>(xr, xi, lane, s_tab);
                     w12_fin_fwd_half<1>(xr, xi, lane, s_tab);
@@ -351,7 +296,7 @@ blind_rotate_w12_kernel(DevParams p, const double2 *__restrict__ bkw, GateAddr g
                         const int sl = 4 * (ch & 3);                      /* slots sl .. sl + 3 of polynomial ch >> 2 */
                         const uint32_t tj = t_acc + (uint32_t)(16 * ch);
                         double2 bn[4];
-                        if (W12_PREFETCH && ch + 1 < 8) {
+                        if (ch + 1 < 8) {
 #pragma unroll
                             for (int r = 0; r < 4; r++) bn[r] = ldg_nc_pinned(bk_r + ((ch + 1) >> 2) * kHalfN + (4 * ((ch + 1) & 3) + r) * 32);
                         }
@@ -362,7 +307,7 @@ blind_rotate_w12_kernel(DevParams p, const double2 *__restrict__ bkw, GateAddr g
                         W12_ST4x4(tj, sacc);
                         if (ch + 1 < 8) {
 #pragma unroll
-                            for (int r = 0; r < 4; r++) bj[r] = W12_PREFETCH ? bn[r] : ldg_nc_pinned(bk_r + ((ch + 1) >> 2) * kHalfN + (4 * ((ch + 1) & 3) + r) * 32);
+                            for (int r = 0; r < 4; r++) bj[r] = bn[r];
                         }
                     }
                     bk_r += kRowElems;
@@ -417,25 +362,37 @@ blind_rotate_w12_kernel(DevParams p, const double2 *__restrict__ bkw, GateAddr g
 
 template <int L>
 static cudaError_t launch_w12_t(const DevParams &p, const double2 *bkw, const GateAddr &ga, const int32_t *baseA, const int32_t *baseB,
-                                int32_t *ext, long long count, cudaStream_t s)
+                                int32_t *ext, long long count, int sms, cudaStream_t s)
 {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t e = cudaFuncSetAttribute(blind_rotate_w12_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, kW12Smem);
     if (e != cudaSuccess) return e;
     const int grid = (int)(count < sms ? count : sms);
-    static const int stagger = [] { const char *e = getenv("IEACHE_W12_STAGGER"); return e ? atoi(e) : 0; }();
-    blind_rotate_w12_kernel<L><<<grid, 32 * kW12Warps, kW12Smem, s>>>(p, bkw, ga, baseA, baseB, ext, stagger);
+    blind_rotate_w12_kernel<L><<<grid, 32 * kW12Warps, kW12Smem, s>>>(p, bkw, ga, baseA, baseB, ext);
     return cudaGetLastError();
 }
 
 cudaError_t launch_blind_rotate_w12(const DevParams &p, const double2 *bkw, const GateAddr &ga, const int32_t *baseA,
-                                    const int32_t *baseB, int32_t *ext, long long count, cudaStream_t s)
+                                    const int32_t *baseB, int32_t *ext, long long count, int sms, cudaStream_t s)
 {
-    if (p.l == 3) return launch_w12_t<3>(p, bkw, ga, baseA, baseB, ext, count, s);
-    if (p.l == 2) return launch_w12_t<2>(p, bkw, ga, baseA, baseB, ext, count, s);
+    if (p.l == 3) return launch_w12_t<3>(p, bkw, ga, baseA, baseB, ext, count, sms, s);
+    if (p.l == 2) return launch_w12_t<2>(p, bkw, ga, baseA, baseB, ext, count, sms, s);
     return cudaErrorInvalidValue;
+}
+
+/* key load: the [slot 8][thread 64] layout of bk_fft_kernel -> [slot 16][lane 32] in the w12_slot_to_K order (same
+ * values, permuted) */
+__global__ void __launch_bounds__(512) bk_relayout_w12_kernel(const double2 *__restrict__ old, double2 *__restrict__ neu, int npoly)
+{
+    const int q = blockIdx.x, idx = threadIdx.x;
+    if (q >= npoly) return;
+    const int K = w12_slot_to_K(idx >> 5, idx & 31);
+    const int t3 = 8 * (K & 7) + ((K >> 3) & 7), r8 = brev3(K >> 6); /* br_core.h: K = b + 8k' + 64 brev3(r), t3 = 8b + k' */
+    neu[(size_t)q * kHalfN + idx] = old[(size_t)q * kHalfN + r8 * 64 + t3];
+}
+cudaError_t launch_bk_relayout_w12(const double2 *bkfft, double2 *bkfft_w, int npoly, cudaStream_t s)
+{
+    bk_relayout_w12_kernel<<<npoly, 512, 0, s>>>(bkfft, bkfft_w, npoly);
+    return cudaGetLastError();
 }
 
 } // namespace ieache

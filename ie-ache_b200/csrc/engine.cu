@@ -68,6 +68,8 @@ struct ieache_ctx {
     int32_t *d_ext = nullptr; size_t ext_cap = 0;      /* extracted samples scratch */
     int32_t *d_stage[4] = {nullptr, nullptr, nullptr, nullptr}; size_t stage_cap[4] = {0, 0, 0, 0};
     int32_t *d_wires = nullptr; size_t wires_cap = 0;
+    LaunchPolicy policy;                 /* which kernel shape a launch of a given size uses: per context, no process-wide state */
+    uint64_t h2d_value_copies = 0, d2h_value_copies = 0; /* operand / result blocks moved by the session calls (tests read them) */
     bool timing = false;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     std::vector<TimedLaunch> timed;
@@ -116,6 +118,13 @@ extern "C" int ieache_ctx_create(int device, ieache_ctx **out)
     CU(upload_twiddles());
     const char *ov = getenv("IEACHE_OVERLAP_KS");
     ctx->overlap_ks = ov && atoi(ov) != 0;
+    ctx->policy.sms = prop.multiProcessorCount;
+    /* developer overrides of the launch policy (tools/); the per-context setter is ieache_ctx_set_tuning */
+    if (const char *e = getenv("IEACHE_CLUSTER_MAX")) ctx->policy.cluster_max = atoll(e);
+    if (const char *e = getenv("IEACHE_WIDE_MAX")) ctx->policy.pair_max = atoll(e);
+    if (const char *e = getenv("IEACHE_W12_MIN")) ctx->policy.w12_min = atoll(e);
+    if (const char *e = getenv("IEACHE_KS_STAGED_MIN")) ctx->policy.ks_staged_min = atoll(e);
+    if (const char *e = getenv("IEACHE_BR_VARIANT")) { const int v = atoi(e); if (v == 0 || v == BR_GROUP || v == BR_W12) ctx->policy.throughput = v; }
     *out = ctx.release();
     return IEACHE_OK;
 }
@@ -179,24 +188,35 @@ extern "C" int ieache_ctx_kernel_times(ieache_ctx *ctx, double *br_ms, double *k
     return IEACHE_OK;
 }
 
-extern "C" int64_t ieache_set_wide_max(int64_t max_gates)
+extern "C" int ieache_ctx_set_tuning(ieache_ctx *ctx, int which, int64_t value, int64_t *old_value)
 {
-    const long long old = get_wide_max();
-    if (max_gates >= 0) set_wide_max(max_gates);
-    return old;
+    if (!ctx) return fail(IEACHE_ERR_ARG, "null ctx");
+    LaunchPolicy &pol = ctx->policy;
+    long long *slot = nullptr;
+    switch (which) {
+    case IEACHE_TUNE_CLUSTER_MAX: slot = &pol.cluster_max; break;
+    case IEACHE_TUNE_PAIR_MAX: slot = &pol.pair_max; break;
+    case IEACHE_TUNE_W12_MIN: slot = &pol.w12_min; break;
+    case IEACHE_TUNE_KS_STAGED_MIN: slot = &pol.ks_staged_min; break;
+    case IEACHE_TUNE_THROUGHPUT_KERNEL:
+        if (old_value) *old_value = pol.throughput;
+        if (value != 0 && value != IEACHE_KERNEL_GROUP && value != IEACHE_KERNEL_W12)
+            return fail(IEACHE_ERR_ARG, "throughput kernel must be 0 (by size), %d or %d (got %lld)", IEACHE_KERNEL_GROUP, IEACHE_KERNEL_W12, (long long)value);
+        pol.throughput = (int)value;
+        return IEACHE_OK;
+    default: return fail(IEACHE_ERR_ARG, "unknown tuning parameter %d", which);
+    }
+    if (old_value) *old_value = *slot;
+    if (value < 0) return fail(IEACHE_ERR_ARG, "negative threshold");
+    *slot = value;
+    return IEACHE_OK;
 }
-extern "C" int ieache_set_throughput_variant(int variant) { return set_throughput_variant(variant); }
-extern "C" int64_t ieache_set_cluster_max(int64_t max_gates)
+extern "C" int ieache_ctx_copy_counts(const ieache_ctx *ctx, uint64_t *h2d_value_blocks, uint64_t *d2h_value_blocks)
 {
-    const long long old = get_cluster_max();
-    if (max_gates >= 0) set_cluster_max(max_gates);
-    return old;
-}
-extern "C" int64_t ieache_set_ks_staged_min(int64_t min_gates)
-{
-    const long long old = get_ks_staged_min();
-    if (min_gates >= 0) set_ks_staged_min(min_gates);
-    return old;
+    if (!ctx) return fail(IEACHE_ERR_ARG, "null ctx");
+    if (h2d_value_blocks) *h2d_value_blocks = ctx->h2d_value_copies;
+    if (d2h_value_blocks) *d2h_value_blocks = ctx->d2h_value_copies;
+    return IEACHE_OK;
 }
 extern "C" int ieache_ctx_timer_start(ieache_ctx *ctx)
 {
@@ -245,8 +265,7 @@ struct ieache_cloudkey {
     ieache_params p{};
     DevParams dp{};
     double2 *bkfft = nullptr; size_t bkfft_bytes = 0;
-    mutable double2 *bkfft_w = nullptr;                /* warp-per-gate layout of the same values, made on first use */
-    mutable int bkfft_w_kind = 0;                      /* 1 plain, 2 folded (unit factors of variant 61 multiplied in) */
+    mutable double2 *bkfft_w = nullptr;                /* the persistent kernel's layout of the same values, made on its first use */
     int32_t *ksk = nullptr; size_t ksk_bytes = 0;
     bool owns = true;
 };
@@ -265,6 +284,13 @@ static void fill_dev_params(const ieache_params &p, DevParams &dp)
 {
     dp.n = p.n; dp.l = p.bk_l; dp.Bgbit = p.bk_Bgbit; dp.ks_t = p.ks_t; dp.ks_basebit = p.ks_basebit;
     dp.mu = 1 << 29; /* modSwitchToTorus32(1, 8) */
+}
+extern "C" int ieache_ctx_pick_kernels(const ieache_ctx *ctx, const ieache_cloudkey *key, int64_t count, int *blind_rotate, int *keyswitch)
+{
+    if (!ctx || !key) return fail(IEACHE_ERR_ARG, "null argument");
+    if (blind_rotate) *blind_rotate = pick_blind_rotate(ctx->policy, count);
+    if (keyswitch) *keyswitch = pick_keyswitch(ctx->policy, key->dp, count);
+    return IEACHE_OK;
 }
 extern "C" int ieache_cloudkey_device_sizes(const ieache_params *p, size_t *bkfft_bytes, size_t *ksk_bytes)
 {
@@ -401,9 +427,14 @@ extern "C" int ieache_keygen(ieache_ctx *ctx, const ieache_params *p, uint64_t s
     int rc = check_params(p);
     if (rc) return rc;
     CU(cudaSetDevice(ctx->device));
+    /* seed 0: both 256-bit stream keys come from the operating system; a non-zero seed gives a reproducible key set
+     * for tests (and no more secrecy than the 64-bit seed) */
+    RngKeys rk;
+    if (seed == 0) { if (rng_keys_from_os(rk)) return fail(IEACHE_ERR_IO, "getrandom failed"); }
+    else rng_keys_from_seed(seed, rk);
     std::vector<int32_t> lwe(p->n), tlwe(1024);
-    host_random_bits(seed, 1, lwe.data(), p->n);
-    host_random_bits(seed, 2, tlwe.data(), 1024);
+    host_key_bits(rk.secret, RNG_LWE_KEY, lwe.data(), p->n);
+    host_key_bits(rk.secret, RNG_TLWE_KEY, tlwe.data(), 1024);
     ieache_secretkey *sk = nullptr;
     if ((rc = ieache_secretkey_import(ctx, p, lwe.data(), tlwe.data(), &sk))) return rc;
     std::unique_ptr<ieache_secretkey, void (*)(ieache_secretkey *)> skg(sk, ieache_secretkey_destroy);
@@ -419,7 +450,7 @@ extern "C" int ieache_keygen(ieache_ctx *ctx, const ieache_params *p, uint64_t s
     CU(cudaMalloc((void **)&d_shat, 512 * sizeof(double2)));
     if (bk_export) CU(cudaMalloc((void **)&d_bk, bk_words * 4));
     if (ksk_export) { CU(cudaMalloc((void **)&d_ks, ksk_words * 4)); CU(cudaMemsetAsync(d_ks, 0, ksk_words * 4, ctx->stream)); }
-    CU(launch_keygen(seed, key->dp, p->ks_stdev, p->bk_stdev, sk->d_lwe_key, sk->d_tlwe_key, d_shat, key->bkfft, key->ksk, d_bk, d_ks, ctx->stream));
+    CU(launch_keygen(rk, key->dp, p->ks_stdev, p->bk_stdev, sk->d_lwe_key, sk->d_tlwe_key, d_shat, key->bkfft, key->ksk, d_bk, d_ks, ctx->stream));
     ctx->launches += 3;
     if (bk_export) CU(cudaMemcpyAsync(bk_export, d_bk, bk_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (ksk_export) CU(cudaMemcpyAsync(ksk_export, d_ks, ksk_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -438,7 +469,10 @@ extern "C" int ieache_sym_encrypt_device(ieache_ctx *ctx, const ieache_secretkey
     int32_t *d_bits = nullptr;
     CU(cudaMalloc((void **)&d_bits, count * 4));
     CU(cudaMemcpyAsync(d_bits, bits, count * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CU(launch_encrypt(seed, sk->p.n, sk->p.ks_stdev, 1 << 29, sk->d_lwe_key, d_bits, out_dev, (long long)count, ctx->stream));
+    RngKeys rk;
+    if (seed == 0) { if (rng_keys_from_os(rk)) return fail(IEACHE_ERR_IO, "getrandom failed"); } /* fresh masks and noise per call */
+    else rng_keys_from_seed(seed, rk);                                                            /* tests only: the same seed repeats the masks */
+    CU(launch_encrypt(rk, sk->p.n, sk->p.ks_stdev, 1 << 29, sk->d_lwe_key, d_bits, out_dev, (long long)count, ctx->stream));
     ctx->launches++;
     CU(cudaStreamSynchronize(ctx->stream));
     cudaFree(d_bits);
@@ -494,13 +528,12 @@ static int run_br(ieache_ctx *ctx, const ieache_cloudkey *key, const GateAddr &g
     TimedLaunch t{};
     { int rcp = apply_l2_persist(ctx, key); if (rcp) return rcp; }
     if (ctx->timing) { CU(cudaEventCreate(&t.a)); CU(cudaEventCreate(&t.b)); t.kind = 0; CU(cudaEventRecord(t.a, ctx->stream)); }
-    const int want_layout = blind_rotate_warp_layout((long long)ga.ntempl * ga.n_inst);
-    if (want_layout && key->bkfft_w_kind != want_layout) {
-        if (!key->bkfft_w) CU(cudaMalloc((void **)&key->bkfft_w, key->bkfft_bytes));
-        CU(launch_bk_relayout_warp(key->bkfft, key->bkfft_w, (int)(key->bkfft_bytes / (kHalfNBytes)), want_layout == 1 ? 0 : want_layout, ctx->stream));
-        key->bkfft_w_kind = want_layout;
+    if (!key->bkfft_w && pick_blind_rotate(ctx->policy, (long long)ga.ntempl * ga.n_inst) == BR_W12) {
+        CU(cudaMalloc((void **)&key->bkfft_w, key->bkfft_bytes));
+        CU(launch_bk_relayout_w12(key->bkfft, key->bkfft_w, (int)(key->bkfft_bytes / (kHalfNBytes)), ctx->stream));
+        ctx->launches++;
     }
-    CU(launch_blind_rotate(key->dp, key->bkfft, want_layout ? key->bkfft_w : nullptr, ga, A, B, ext ? ext : ctx->d_ext, ext_base, ctx->stream));
+    CU(launch_blind_rotate(key->dp, ctx->policy, key->bkfft, key->bkfft_w, ga, A, B, ext ? ext : ctx->d_ext, ext_base, ctx->stream));
     if (ctx->timing) { CU(cudaEventRecord(t.b, ctx->stream)); ctx->timed.push_back(t); }
     ctx->launches++;
     return IEACHE_OK;
@@ -511,7 +544,7 @@ static int run_ks(ieache_ctx *ctx, const ieache_cloudkey *key, const GateAddr &g
     TimedLaunch t{};
     if (!st) st = ctx->stream;
     if (ctx->timing) { CU(cudaEventCreate(&t.a)); CU(cudaEventCreate(&t.b)); t.kind = 1; CU(cudaEventRecord(t.a, st)); }
-    CU(launch_keyswitch(key->dp, key->ksk, ga, out, ext ? ext : ctx->d_ext, pair_offset, cst_post, st));
+    CU(launch_keyswitch(key->dp, ctx->policy, key->ksk, ga, out, ext ? ext : ctx->d_ext, pair_offset, cst_post, st));
     if (ctx->timing) { CU(cudaEventRecord(t.b, st)); ctx->timed.push_back(t); }
     ctx->launches++;
     if (ctx->timed.size() > 4096) return drain_timed(ctx);
@@ -903,7 +936,9 @@ extern "C" int ieache_session_compute_batch(ieache_session *s, size_t count, con
         const int32_t n2 = dec32(s->nbit, o2);                                               /* cloud.c:780-796 */
         if (n1 == 2) n1 = 1;
         const int32_t int_negative = n1 + n2;
-        enc32(s->nbit, int_negative == 3 ? 4 : int_negative, ans);                           /* cloud.c:812-826 */
+        /* cloud.c:812-826: 1 -> 1, 2 -> 2, 3 -> 4, anything else (an operand block that already carries code 4 from an
+         * earlier operator of a chain) -> 0 */
+        enc32(s->nbit, int_negative == 1 ? 1 : int_negative == 2 ? 2 : int_negative == 3 ? 4 : 0, ans);
         int32_t int_bit;
         if (int_op == 4) { int_bit = std::max(int_bit1, int_bit2); enc32(s->nbit, int_bit * 2, ans + B); }   /* cloud.c:833-843 */
         else if (int_bit1 >= int_bit2) { int_bit = int_bit1; memcpy(ans + B, o1 + B, B * 4); }

@@ -1,24 +1,20 @@
 /*
- * kernels.cu — sm_100a kernels of the gate-bootstrapping engine.
+ * kernels.cu — sm_100a kernels of the gate-bootstrapping engine (all but the persistent blind rotation, br_w12.cu).
  *
- *   blind_rotate_kernel  fused: linear gate pre-combination -> modSwitch -> test-vector init ->
- *                        n x { (X^abar-1)*ACC, gadget decomposition, (k+1)l forward transforms,
- *                        pointwise MAC with BK_i, k+1 inverse transforms, ACC += } -> SampleExtract
- *                        (replaces libtfhe tfhe_bootstrap_woKS_FFT reached from
- *                        Cloud/cloud.c:30,32,38,40,43 — SURVEY.md §8 a14, App. A)
- *   keyswitch_kernel     lweKeySwitch as a vectorised gather-accumulate over a compacted digit list
- *   bk_fft_kernel        key load: coefficient BK -> transform-domain layout (libtfhe does this on
- *                        the CPU inside new_tfheGateBootstrappingCloudKeySet_fromFile, Cloud/cloud.c:657)
- *
- * One 64-thread group owns one gate: ACC (8 KB), two exchange buffers (2 x 9 KB) and the
- * mod-switched mask live in shared memory; the transform-domain accumulators (2 x 8 complex)
- * live in registers.  Groups only use their own named barrier, so a CTA is just a container
- * that makes neighbouring gates share BK_i lines in L1.
+ *   blind_rotate_{cluster,pair,}_kernel   fused: linear gate pre-combination -> modSwitch -> test-vector init ->
+ *                        n x { (X^abar-1)*ACC, gadget decomposition, (k+1)l forward transforms, pointwise MAC with
+ *                        BK_i, k+1 inverse transforms, ACC += } -> SampleExtract (replaces libtfhe
+ *                        tfhe_bootstrap_woKS_FFT reached from Cloud/cloud.c:30,32,38,40,43 — SURVEY.md §8 a14, App. A)
+ *                        in three shapes by launch size: one gate on a 2-CTA cluster, one gate on two groups of a
+ *                        CTA, one gate per 64-thread CTA
+ *   keyswitch_{cluster,staged,}_kernel    lweKeySwitch: 8-CTA cluster per gate / TMA-staged row blocks shared by 12
+ *                        gates / per-gate gather over a compacted digit list
+ *   bk_fft_kernel        key load: coefficient BK -> transform-domain layout (libtfhe does this on the CPU inside
+ *                        new_tfheGateBootstrappingCloudKeySet_fromFile, Cloud/cloud.c:657)
+ *   pick_blind_rotate / pick_keyswitch    which shape a launch of a given size uses (LaunchPolicy, per context)
  */
 #include "kernels.h"
 #include "br_core.h"
-#include "br_warp.h"
-
 #include <cooperative_groups.h>
 #include <math.h>
 #include <stdlib.h>
@@ -28,30 +24,12 @@ namespace ieache {
 
 __device__ Tw d_tw2[8];
 __device__ Tw d_tw3[64];
-__device__ Tw16 d_tw16[16];   /* warp layout: pass-2 twiddles by lane & 15 */
-__device__ FinTw d_fin[32];   /* warp layout: final-stage twiddles by lane */
-__device__ Tw16g d_tw16g[32]; /* folded forward variant: pass-2 twiddles by lane */
-__device__ FinTw d_finf[32];  /* folded forward variant: final-stage w by lane */
 
 cudaError_t upload_twiddles()
 {
     Tw tw2[8], tw3[64];
     host_twiddles(tw2, tw3);
     cudaError_t e = cudaMemcpyToSymbol(d_tw2, tw2, sizeof(tw2));
-    if (e != cudaSuccess) return e;
-    Tw16 tw16[16];
-    FinTw fin[32];
-    host_twiddles_warp(tw16, fin);
-    e = cudaMemcpyToSymbol(d_tw16, tw16, sizeof(tw16));
-    if (e != cudaSuccess) return e;
-    e = cudaMemcpyToSymbol(d_fin, fin, sizeof(fin));
-    if (e != cudaSuccess) return e;
-    Tw16g tw16g[32];
-    FinTw finf[32];
-    host_twiddles_warp_folded(tw16g, finf);
-    e = cudaMemcpyToSymbol(d_tw16g, tw16g, sizeof(tw16g));
-    if (e != cudaSuccess) return e;
-    e = cudaMemcpyToSymbol(d_finf, finf, sizeof(finf));
     if (e != cudaSuccess) return e;
     e = upload_twiddles_w12();
     if (e != cudaSuccess) return e;
@@ -69,11 +47,9 @@ cudaError_t twiddle_ptrs(const Tw **tw2, const Tw **tw3)
  * reserves 2 barriers instead of 16, worth ~5 % in the throughput kernel); a switch over immediate ids was
  * measured slower than the register form for the multi-group kernels. */
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-constexpr int kCtaBarrier = -1; /* group id meaning "the gate's threads are spread over every warp of the CTA" */
 __device__ __forceinline__ void group_sync(int grp)
 {
-    if (grp < 0) __syncthreads();
-    else asm volatile("bar.sync %0, 64;" ::"r"(grp + 1) : "memory");
+    asm volatile("bar.sync %0, 64;" ::"r"(grp + 1) : "memory");
 }
 
 /* forward transform of the 8 points in registers; leaves evaluations in x[r] of thread t3 = tid */
@@ -157,46 +133,22 @@ constexpr int kBufBytes = kBufElems * 16;
 constexpr int kAbarBytes = 2080;
 constexpr int kGroupSmem = kAccBytes + 2 * kBufBytes + kAbarBytes; /* 28704 */
 
-/* L = gadget length, G = gates (64-thread groups) per CTA, MINB = CTAs per SM the register
- * allocation is tuned for, ROLL = 0 unrolled step body, 1 rolled over both loops, 2 rolled over digits only, 3 over polynomials only: the
- * step body fits the 32 KB instruction cache (the fully unrolled body is ~60 KB of SASS) */
-template <int L, int G, int MINB, int ROLL, int NOBK = 0, bool LOCK = false, bool SPREAD = false, bool ACCREG = false>
-__device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
-                    const int32_t *__restrict__ baseB, int32_t *__restrict__ ext);
-
-template <int L, int G, int MINB, int ROLL, int NOBK = 0, bool LOCK = false, bool SPREAD = false, bool ACCREG = false>
-__global__ void __launch_bounds__(64 * G, MINB)
+/* One 64-thread group (CTA) per gate, 4 CTAs per SM: the transform-domain accumulators (2 x 8 complex) and, with
+ * ACCREG, the 32 ACC coefficients a thread reads unrotated and updates live in registers.  L = gadget length;
+ * ROLL = 0 unrolled step body, 2 rolled over the digits (half the code).  Used for launches of 297..~900 gates, where
+ * its 592-gate wave is a better fit than the 1 776-gate wave of the persistent kernel (br_w12.cu). */
+template <int L, int ROLL, bool ACCREG>
+__global__ void __launch_bounds__(64, 4)
 blind_rotate_kernel(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
-                    const int32_t *__restrict__ baseB, int32_t *__restrict__ ext, int stagger, int sms)
-{
-    /* CTAs that start together run the same program in phase: their FP64 bursts collide and their exchange phases
-     * leave the pipe idle together.  The first wave starts staggered; later CTAs inherit the offsets. */
-    if (stagger > 0 && (int)blockIdx.x < MINB * sms) {
-        const long long wait = (long long)(blockIdx.x / sms) * stagger, t0 = clock64();
-        while (clock64() - t0 < wait) { }
-    }
-    blind_rotate_body<L, G, MINB, ROLL, NOBK, LOCK, SPREAD, ACCREG>(p, bkfft, ga, baseA, baseB, ext);
-}
-template <int L, int G, int MINB, int ROLL, int NOBK, bool LOCK, bool SPREAD, bool ACCREG>
-__device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
                     const int32_t *__restrict__ baseB, int32_t *__restrict__ ext)
 {
-    static_assert(!SPREAD || (LOCK && (G == 2 || G == 4)), "SPREAD: 2 or 4 lock-step gates per CTA");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    /* SPREAD: every warp holds 32/G lanes of each of the CTA's G gates (gate thread tid = warp * 32/G + lane % (32/G)),
-     * so the lanes of different gates that own the same transform slots read the same BK_i addresses in the same
-     * instruction: one 128-byte wavefront serves G gates (784 -> 784/G LSU wavefronts per gate-step for BK, and
-     * 1/G of the L2->L1 traffic).  The price: the G gates run in lock step on CTA-wide barriers. */
-    constexpr int LPG = 32 / (SPREAD ? G : 1);
-    const int grp = SPREAD ? (int)((threadIdx.x & 31) / LPG) : ((G == 1) ? 0 : (threadIdx.x >> 6));
-    const int tid = SPREAD ? (int)((threadIdx.x >> 5) * LPG + (threadIdx.x & (LPG - 1))) : ((G == 1) ? threadIdx.x : (threadIdx.x & 63));
-    const int bar = SPREAD ? kCtaBarrier : grp; /* barrier domain of one transform */
-    int g = blockIdx.x * G + grp;
-    const bool active = g < ga.ntempl * ga.n_inst;
-    if (!LOCK && !active) return; /* whole group leaves; groups never share a barrier */
-    if (!active) g = ga.ntempl * ga.n_inst - 1; /* lock-step CTAs: idle groups shadow the last gate, write nothing */
+    constexpr int grp = 0;
+    const int tid = threadIdx.x;
+    const int g = blockIdx.x;
+    if (g >= ga.ntempl * ga.n_inst) return;
 
-    unsigned char *base = smem_raw + (size_t)grp * kGroupSmem;
+    unsigned char *base = smem_raw;
     int32_t *acc = reinterpret_cast<int32_t *>(base);
     cd *bufA = reinterpret_cast<cd *>(base + kAccBytes);
     cd *bufB = reinterpret_cast<cd *>(base + kAccBytes + kBufBytes);
@@ -219,7 +171,7 @@ __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__
             abar[i] = (uint16_t)modswitch_2N(v);
         }
     }
-    group_sync(bar);
+    group_sync(grp);
     /* 2. ACC = (0, X^{2N-bbar} * mu * (1 + X + ... + X^{N-1})) */
     {
         const int bbar = abar[n];
@@ -231,7 +183,7 @@ __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__
             acc[kN + j] = ((j < ar) != flip) ? -p.mu : p.mu;
         }
     }
-    group_sync(bar);
+    group_sync(grp);
 
     const Tw w1 = tw_pass1();
     const Tw w2 = d_tw2[tid >> 3];
@@ -247,7 +199,7 @@ __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__
     constexpr int kBkStride = 2 * L * kRowElems; /* elements per BK_i */
     int toggle = 0;
     /* ACCREG: the 32 ACC coefficients this thread reads unrotated and later updates stay in registers, so a step
-     * only loads the rotated operand and stores the updated value (-128 of 3 135 LSU wavefronts per gate-step) */
+     * only loads the rotated operand and stores the updated value */
     int32_t areg[2][16];
     if (ACCREG) {
 #pragma unroll
@@ -258,19 +210,14 @@ __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__
 
     /* 3. n CMux steps */
     for (int i = 0; i < n; i++) {
-        /* LOCK: all gates of the CTA enter step i together, so BK_i is fetched from L2 once per CTA and the
-         * other groups hit it in L1 */
-        if (LOCK && !SPREAD) __syncthreads();
         const int a = abar[i];
-        /* a = 0 adds exactly zero (all digits of (X^0 - 1) ACC are 0); the skip is only a shortcut, and the gates
-         * of a SPREAD CTA share barriers, so they all run the step */
-        if (!SPREAD && a == 0) continue; /* uniform inside the group */
+        if (a == 0) continue; /* (X^0 - 1) ACC = 0: the step adds exactly zero; uniform inside the group */
         double s0r[8], s0i[8], s1r[8], s1i[8];
 #pragma unroll
         for (int r = 0; r < 8; r++) { s0r[r] = 0.0; s0i[r] = 0.0; s1r[r] = 0.0; s1i[r] = 0.0; }
         const double2 *bk_r = bkfft + (size_t)i * kBkStride + tid;
 
-#pragma unroll((ROLL == 1 || ROLL == 3) ? 1 : 2)
+#pragma unroll
         for (int q = 0; q < 2; q++) {
             int32_t c[16];
             if (ACCREG) {
@@ -284,46 +231,31 @@ __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__
             } else {
                 rot_minus_one(acc + q * kN, tid, a, c);
             }
-#pragma unroll((ROLL == 1 || ROLL == 2) ? 1 : L)
+#pragma unroll(ROLL == 2 ? 1 : L)
             for (int pp = 0; pp < L; pp++) {
                 const int shift = 32 - (pp + 1) * Bgbit;
                 double xr[8], xi[8];
                 cd *buf = toggle ? bufB : bufA;
                 toggle ^= 1;
-                if (ACCREG) { /* the default variant also starts the transform from the integer digits */
+                if (ACCREG) { /* the transform starts from the integer digits (cheaper first stage, br_core.h) */
                     int32_t dr[8], di[8];
 #pragma unroll
                     for (int m = 0; m < 8; m++) {
                         dr[m] = digit_i32(c[m], offset, shift, maskBg, halfBg);
                         di[m] = digit_i32(c[8 + m], offset, shift, maskBg, halfBg);
                     }
-                    fwd_transform_digits(dr, di, xr, xi, buf, tid, bar, w1, w2, w3);
+                    fwd_transform_digits(dr, di, xr, xi, buf, tid, grp, w1, w2, w3);
                 } else {
 #pragma unroll
-                for (int m = 0; m < 8; m++) {
-                    xr[m] = digit_f64(c[m], offset, shift, maskBg, halfBg);
-                    xi[m] = digit_f64(c[8 + m], offset, shift, maskBg, halfBg);
-                }
-                if (NOBK == 3) { /* timing experiment (wrong results): forward transform without the butterflies of pass 2 */
-                    pass_fwd(xr, xi, w1);
-                    st_pass1(buf, tid, xr, xi);
-                    group_sync(bar);
-                    ld_pass2(buf, tid, xr, xi);
-                    st_pass2(buf, tid, xr, xi);
-                    group_sync(bar);
-                    ld_pass3(buf, tid, xr, xi);
-                    pass_fwd(xr, xi, w3);
-                } else {
-                    fwd_transform(xr, xi, buf, tid, bar, w1, w2, w3);
-                }
+                    for (int m = 0; m < 8; m++) {
+                        xr[m] = digit_f64(c[m], offset, shift, maskBg, halfBg);
+                        xi[m] = digit_f64(c[8 + m], offset, shift, maskBg, halfBg);
+                    }
+                    fwd_transform(xr, xi, buf, tid, grp, w1, w2, w3);
                 }
 #pragma unroll
                 for (int r = 0; r < 8; r++) {
-                    /* NOBK (timing experiments, wrong results): 1 = no loads at all, 2 = the same 16-byte loads from a
-                     * 16 KB shared-memory row (what a TMA-staged BK_i would cost the LSU, without its L2 latency) */
-                    const double2 *fake = reinterpret_cast<const double2 *>(smem_raw + (size_t)G * kGroupSmem) + tid;
-                    const double2 b0 = NOBK == 1 ? make_double2(1.0 + r, 0.5) : (NOBK == 2 ? fake[r * 64] : __ldg(bk_r + r * 64));
-                    const double2 b1 = NOBK == 1 ? make_double2(0.25, 2.0 - r) : (NOBK == 2 ? fake[kHalfN + r * 64] : __ldg(bk_r + kHalfN + r * 64));
+                    const double2 b0 = __ldg(bk_r + r * 64), b1 = __ldg(bk_r + kHalfN + r * 64);
                     cmac(s0r[r], s0i[r], xr[r], xi[r], b0.x, b0.y);
                     cmac(s1r[r], s1i[r], xr[r], xi[r], b1.x, b1.y);
                 }
@@ -335,7 +267,7 @@ __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__
         for (int j = 0; j < 2; j++) {
             cd *buf = toggle ? bufB : bufA;
             toggle ^= 1;
-            inv_transform(s0r, s0i, buf, tid, bar, w1, w2, w3);
+            inv_transform(s0r, s0i, buf, tid, grp, w1, w2, w3);
             int32_t *accj = acc + j * kN;
             if (ACCREG) {
 #pragma unroll
@@ -355,463 +287,13 @@ __device__ __forceinline__ void blind_rotate_body(DevParams p, const double2 *__
 #pragma unroll
             for (int r = 0; r < 8; r++) { s0r[r] = s1r[r]; s0i[r] = s1i[r]; }
         }
-        group_sync(bar);
-    }
-
-    /* 4. SampleExtract at index 0 */
-    if (!active) return;
-    int32_t *o = ext + (size_t)g * kExtStride;
-    for (int j = tid; j < kN; j += 64) o[j] = (j == 0) ? acc[0] : -acc[kN - j];
-    if (tid == 0) o[kN] = acc[kN];
-}
-
-/* ---- throughput variant with the transform-domain accumulators in tensor memory ----
- * The 784 LSU wavefronts a gate-step spends on BK_i are per gate because a thread has no registers left to serve a
- * second gate: 64 of its 252 registers are accumulators.  Here they live in TMEM (tcgen05.st / tcgen05.ld, 32x32b:
- * every thread owns its lane's columns; ~5 KB/clk/SM of read bandwidth measured by tools/tmem_probe.cu), one
- * 64-thread group owns GP gates, and each BK_i row is loaded into registers once and used for the GP forward
- * transforms of that row: BK wavefronts and L1/L2 traffic per gate drop by GP.
- * CTA = one 64-thread group (TMEM lanes 0..63), 4 CTAs per SM, GP * 64 columns per CTA (512 in all at GP = 2). */
-template <int GP> __host__ __device__ constexpr int tmem_group_smem() { return GP * (kAccBytes + kAbarBytes) + 2 * kBufBytes; }
-
-/* 32 columns = 16 doubles per thread (one polynomial's 8 slots x {re, im}); the b32 halves are packed inside the asm
- * so that ptxas allocates them as the register pairs of the doubles (no move instructions) */
-#define IE_TMEM_LD16D(taddr, d) asm volatile("{\n\t.reg .b32 t<32>;\n\t" \
-    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {t0,t1,t2,t3,t4,t5,t6,t7,t8,t9,t10,t11,t12,t13,t14,t15,t16,t17,t18,t19,t20,t21,t22,t23,t24,t25,t26,t27,t28,t29,t30,t31}, [%16];\n\t" \
-    "tcgen05.wait::ld.sync.aligned;\n\t" \
-    "mov.b64 %0, {t0,t1};\n\tmov.b64 %1, {t2,t3};\n\tmov.b64 %2, {t4,t5};\n\tmov.b64 %3, {t6,t7};\n\tmov.b64 %4, {t8,t9};\n\tmov.b64 %5, {t10,t11};\n\tmov.b64 %6, {t12,t13};\n\tmov.b64 %7, {t14,t15};\n\tmov.b64 %8, {t16,t17};\n\tmov.b64 %9, {t18,t19};\n\tmov.b64 %10, {t20,t21};\n\tmov.b64 %11, {t22,t23};\n\tmov.b64 %12, {t24,t25};\n\tmov.b64 %13, {t26,t27};\n\tmov.b64 %14, {t28,t29};\n\tmov.b64 %15, {t30,t31};\n\t}" \
-    : "=d"(d[0]),"=d"(d[1]),"=d"(d[2]),"=d"(d[3]),"=d"(d[4]),"=d"(d[5]),"=d"(d[6]),"=d"(d[7]),"=d"(d[8]),"=d"(d[9]),"=d"(d[10]),"=d"(d[11]),"=d"(d[12]),"=d"(d[13]),"=d"(d[14]),"=d"(d[15]) : "r"(taddr) : "memory")
-#define IE_TMEM_ST16D(taddr, d) asm volatile("{\n\t.reg .b32 t<32>;\n\t" \
-    "mov.b64 {t0,t1}, %1;\n\tmov.b64 {t2,t3}, %2;\n\tmov.b64 {t4,t5}, %3;\n\tmov.b64 {t6,t7}, %4;\n\tmov.b64 {t8,t9}, %5;\n\tmov.b64 {t10,t11}, %6;\n\tmov.b64 {t12,t13}, %7;\n\tmov.b64 {t14,t15}, %8;\n\tmov.b64 {t16,t17}, %9;\n\tmov.b64 {t18,t19}, %10;\n\tmov.b64 {t20,t21}, %11;\n\tmov.b64 {t22,t23}, %12;\n\tmov.b64 {t24,t25}, %13;\n\tmov.b64 {t26,t27}, %14;\n\tmov.b64 {t28,t29}, %15;\n\tmov.b64 {t30,t31}, %16;\n\t" \
-    "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {t0,t1,t2,t3,t4,t5,t6,t7,t8,t9,t10,t11,t12,t13,t14,t15,t16,t17,t18,t19,t20,t21,t22,t23,t24,t25,t26,t27,t28,t29,t30,t31};\n\t}" \
-    :: "r"(taddr), "d"(d[0]),"d"(d[1]),"d"(d[2]),"d"(d[3]),"d"(d[4]),"d"(d[5]),"d"(d[6]),"d"(d[7]),"d"(d[8]),"d"(d[9]),"d"(d[10]),"d"(d[11]),"d"(d[12]),"d"(d[13]),"d"(d[14]),"d"(d[15]) : "memory")
-
-template <int L, int GP, int MINB = 4>
-__global__ void __launch_bounds__(64, MINB)
-blind_rotate_tmem_kernel(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
-                         const int32_t *__restrict__ baseB, int32_t *__restrict__ ext)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ uint32_t tmem_base_slot;
-    constexpr int kCols = GP * 64;                        /* per thread: GP gates x 2 polynomials x 8 slots x 4 words */
-    constexpr int grp = 0;                                /* one group per CTA: compile-time barrier id */
-    const int tid = threadIdx.x, warp = threadIdx.x >> 5;
-    unsigned char *base = smem_raw;
-    int32_t *acc = reinterpret_cast<int32_t *>(base);                                    /* [GP][2][1024] */
-    uint16_t *abar = reinterpret_cast<uint16_t *>(base + GP * kAccBytes);                /* [GP][1040] */
-    cd *bufA = reinterpret_cast<cd *>(base + GP * (kAccBytes + kAbarBytes)), *bufB = bufA + kBufElems;
-
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "n"(kCols));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    const int n = p.n;
-    const long long total = (long long)ga.ntempl * ga.n_inst;
-    const long long g_first = (long long)blockIdx.x * GP;
-    /* 1. linear pre-combination + modSwitch, 2. ACC init, for the GP gates of this group (idle slots shadow the last gate) */
-#pragma unroll
-    for (int k = 0; k < GP; k++) {
-        long long g = g_first + k;
-        if (g >= total) g = total - 1;
-        const int e = (int)(g / ga.ntempl), t = (int)(g - (long long)e * ga.ntempl);
-        GateT gt = ga.uni;
-        if (ga.tmpl) gt = ga.tmpl[t]; else { gt.in0 = (gt.in0 >= 0) ? t : -1; gt.in1 = (gt.in1 >= 0) ? t : -1; }
-        const size_t blk = (size_t)e * ga.inst_samples;
-        const int32_t *in0 = gt.in0 >= 0 ? baseA + (blk + gt.in0) * ga.stride : nullptr;
-        const int32_t *in1 = gt.in1 >= 0 ? baseB + (blk + gt.in1) * ga.stride : nullptr;
-        const int32_t c0 = gt.c0, c1 = gt.c1, cst = gt.cst_mu * p.mu;
-        for (int i = tid; i <= n; i += 64) {
-            int32_t v = (i == n) ? cst : 0;
-            if (in0) v += c0 * __ldg(in0 + i);
-            if (in1) v += c1 * __ldg(in1 + i);
-            abar[k * 1040 + i] = (uint16_t)modswitch_2N(v);
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;");
-    const uint32_t taddr = tmem_base_slot + ((uint32_t)(warp * 32) << 16);
-#pragma unroll
-    for (int k = 0; k < GP; k++) {
-        const int bbar = abar[k * 1040 + n];
-        const int a = (2 * kN - bbar) & (2 * kN - 1), ar = a & (kN - 1);
-        const bool flip = a >= kN;
-        for (int j = tid; j < kN; j += 64) {
-            acc[k * 2 * kN + j] = 0;
-            acc[k * 2 * kN + kN + j] = ((j < ar) != flip) ? -p.mu : p.mu;
-        }
-    }
-    group_sync(grp);
-
-    const Tw w1 = tw_pass1(), w2 = d_tw2[tid >> 3], w3 = d_tw3[tid];
-    const int Bgbit = p.Bgbit;
-    const uint32_t maskBg = (1u << Bgbit) - 1;
-    const int32_t halfBg = 1 << (Bgbit - 1);
-    uint32_t offset = 0;
-#pragma unroll
-    for (int i = 1; i <= L; i++) offset += (uint32_t)halfBg << (32 - i * Bgbit);
-    constexpr int kRowElems = 2 * kHalfN, kBkStride = 2 * L * kRowElems;
-    int toggle = 0;
-
-    for (int i = 0; i < n; i++) {
-        const double2 *bk_r = bkfft + (size_t)i * kBkStride + tid;
-#pragma unroll 1
-        for (int q = 0; q < 2; q++) {
-            int32_t c[GP][16];
-#pragma unroll
-            for (int k = 0; k < GP; k++) rot_minus_one(acc + (k * 2 + q) * kN, tid, abar[k * 1040 + i], c[k]);
-#pragma unroll 1
-            for (int pp = 0; pp < L; pp++) {
-                const int shift = 32 - (pp + 1) * Bgbit;
-                /* this row of BK_i: once for the GP gates of the group.  With more than 4 CTAs per SM there are no
-                 * registers to hold it across a transform: it is then requested per polynomial right before use */
-                double2 b0[8], b1[8];
-                if (MINB <= 4) {
-#pragma unroll
-                    for (int r = 0; r < 8; r++) { b0[r] = __ldg(bk_r + r * 64); b1[r] = __ldg(bk_r + kHalfN + r * 64); }
-                }
-                const double2 *bk_row = bk_r;
-                bk_r += kRowElems;
-                const bool first = (q == 0) && (pp == 0);
-#pragma unroll
-                for (int k = 0; k < GP; k++) {
-                    double xr[8], xi[8];
-#pragma unroll
-                    for (int m = 0; m < 8; m++) {
-                        xr[m] = digit_f64(c[k][m], offset, shift, maskBg, halfBg);
-                        xi[m] = digit_f64(c[k][8 + m], offset, shift, maskBg, halfBg);
-                    }
-                    cd *buf = toggle ? bufB : bufA;
-                    toggle ^= 1;
-                    fwd_transform(xr, xi, buf, tid, grp, w1, w2, w3);
-                    /* accumulate into TMEM (layout per gate and polynomial: 8 slots x {re, im}), one output polynomial
-                     * at a time; stores of the previous row to the same columns are long complete, the wait only
-                     * orders them */
-                    if (!first) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-#pragma unroll
-                    for (int j = 0; j < 2; j++) {
-                        double sacc[16];
-                        const uint32_t tj = taddr + (uint32_t)((k * 2 + j) * 32);
-                        double2 bj[8];
-#pragma unroll
-                        for (int r = 0; r < 8; r++) bj[r] = (MINB <= 4) ? (j ? b1[r] : b0[r]) : __ldg(bk_row + j * kHalfN + r * 64);
-                        if (!first) {
-                            IE_TMEM_LD16D(tj, sacc);
-                        } else {
-#pragma unroll
-                            for (int r = 0; r < 16; r++) sacc[r] = 0.0;
-                        }
-#pragma unroll
-                        for (int r = 0; r < 8; r++) cmac(sacc[2 * r], sacc[2 * r + 1], xr[r], xi[r], bj[r].x, bj[r].y);
-                        IE_TMEM_ST16D(tj, sacc);
-                    }
-                }
-            }
-        }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        /* inverse transforms and ACC update */
-#pragma unroll 1
-        for (int kj = 0; kj < 2 * GP; kj++) {
-            double sv[16];
-            const uint32_t t0 = taddr + (uint32_t)(kj * 32);
-            IE_TMEM_LD16D(t0, sv);
-            double sr[8], si[8];
-#pragma unroll
-            for (int r = 0; r < 8; r++) { sr[r] = sv[2 * r]; si[r] = sv[2 * r + 1]; }
-            cd *buf = toggle ? bufB : bufA;
-            toggle ^= 1;
-            inv_transform(sr, si, buf, tid, grp, w1, w2, w3);
-            int32_t *accj = acc + (size_t)kj * kN;
-#pragma unroll
-            for (int m = 0; m < 8; m++) {
-                accj[tid + 64 * m] += round_to_torus(sr[m]);
-                accj[tid + 64 * m + 512] += round_to_torus(si[m]);
-            }
-        }
         group_sync(grp);
     }
 
-    /* SampleExtract */
-#pragma unroll
-    for (int k = 0; k < GP; k++) {
-        const long long g = g_first + k;
-        if (g < total) {
-            int32_t *o = ext + (size_t)g * kExtStride;
-            const int32_t *ak = acc + k * 2 * kN;
-            for (int j = tid; j < kN; j += 64) o[j] = (j == 0) ? ak[0] : -ak[kN - j];
-            if (tid == 0) o[kN] = ak[kN];
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_slot), "n"(kCols));
-}
-
-template <int L, int GP, int MINB = 4>
-static cudaError_t launch_br_tmem(const DevParams &p, const double2 *bkfft, const GateAddr &ga, const int32_t *baseA,
-                                  const int32_t *baseB, int32_t *ext, long long count, cudaStream_t s)
-{
-    constexpr int smem = tmem_group_smem<GP>();
-    cudaError_t e = cudaFuncSetAttribute(blind_rotate_tmem_kernel<L, GP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    const int grid = (int)((count + GP - 1) / GP);
-    blind_rotate_tmem_kernel<L, GP, MINB><<<grid, 64, smem, s>>>(p, bkfft, ga, baseA, baseB, ext);
-    return cudaGetLastError();
-}
-
-/* ---- throughput variant with one WARP per gate (br_warp.h): 16 points per lane, one shared-memory exchange and one
- * shuffle stage per transform (160 LSU wavefronts instead of 256), no CTA barrier in the loop, accumulators in TMEM
- * (2 polynomials x 16 slots x 4 words = 128 columns per lane).  CTA = 4 warps = 4 gates = the four lane quadrants of
- * the CTA's 128 TMEM columns; 2 CTAs per SM.  Reads the bootstrapping key in the layout [row][poly][slot 16][lane 32]
- * that bk_relayout_warp_kernel derives from the [slot 8][thread 64] one at key load (same values, permuted). */
-constexpr int kWarpGateSmem = kAccBytes + kWarpBufElems * 16 + kAbarBytes; /* 18 720 B per gate */
-
-__global__ void __launch_bounds__(512) bk_relayout_warp_kernel(const double2 *__restrict__ old, double2 *__restrict__ neu, int npoly, int folded)
-{
-    const int q = blockIdx.x, idx = threadIdx.x;
-    if (q >= npoly) return;
-    const int p = idx >> 5, lane = idx & 31;
-    const int K = folded == 3 ? w12_slot_to_K(p, lane) : warp_slot_to_K(p, lane); /* 3: plain values in the 12-warp kernel's slot order */
-    const int t3 = 8 * (K & 7) + ((K >> 3) & 7), r8 = brev3(K >> 6); /* br_core.h: K = b + 8k' + 64 brev3(r), t3 = 8b + k' */
-    double2 v = old[(size_t)q * kHalfN + r8 * 64 + t3];
-    if (folded == 2) { /* the unit factor the select-free forward transform leaves on the Lpar = 1 lanes (br_warp.h) */
-        double fr, fi;
-        folded_bk_factor(d_finf[lane], p, lane, fr, fi);
-        v = make_double2(v.x * fr - v.y * fi, v.x * fi + v.y * fr);
-    }
-    neu[(size_t)q * kHalfN + idx] = v;
-}
-cudaError_t launch_bk_relayout_warp(const double2 *bkfft, double2 *bkfft_w, int npoly, int folded, cudaStream_t s)
-{
-    bk_relayout_warp_kernel<<<npoly, 512, 0, s>>>(bkfft, bkfft_w, npoly, folded);
-    return cudaGetLastError();
-}
-
-__device__ __forceinline__ void warp_exchange8(const double (&sr)[8], const double (&si)[8], double (&rr)[8], double (&ri)[8])
-{
-#pragma unroll
-    for (int s = 0; s < 8; s++) { rr[s] = __shfl_xor_sync(0xffffffffu, sr[s], 16); ri[s] = __shfl_xor_sync(0xffffffffu, si[s], 16); }
-}
-
-template <int L, bool FOLD = false>
-__global__ void __launch_bounds__(128, 2)
-blind_rotate_warp_kernel(DevParams p, const double2 *__restrict__ bkw, GateAddr ga, const int32_t *__restrict__ baseA,
-                         const int32_t *__restrict__ baseB, int32_t *__restrict__ ext)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ uint32_t tmem_base_slot;
-    __shared__ double s_finr[8][32], s_fini[8][32]; /* final-stage twiddles [s][lane]: 32 registers per thread otherwise */
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, lpar = lane >> 4;
-    __shared__ double s_finfr[FOLD ? 8 : 1][32], s_finfi[FOLD ? 8 : 1][32]; /* folded variant: forward-stage w */
-    __shared__ double s_tw2[FOLD ? 16 : 1][16];                             /* folded variant: plain pass-2 twiddles for the inverse */
-    if (warp == 1) {
-#pragma unroll
-        for (int s8 = 0; s8 < 8; s8++) { s_finr[s8][lane] = d_fin[lane].zr[s8]; s_fini[s8][lane] = d_fin[lane].zi[s8]; }
-        if (FOLD) {
-#pragma unroll
-            for (int s8 = 0; s8 < 8; s8++) { s_finfr[s8][lane] = d_finf[lane].zr[s8]; s_finfi[s8][lane] = d_finf[lane].zi[s8]; }
-        }
-    }
-    if (FOLD && warp == 2 && lane < 16) {
-        const double *src = reinterpret_cast<const double *>(&d_tw16[lane]);
-#pragma unroll
-        for (int v = 0; v < 16; v++) s_tw2[v][lane] = src[v];
-    }
-    unsigned char *base = smem_raw + (size_t)warp * kWarpGateSmem;
-    int32_t *acc = reinterpret_cast<int32_t *>(base);
-    cd *buf = reinterpret_cast<cd *>(base + kAccBytes);
-    uint16_t *abar = reinterpret_cast<uint16_t *>(base + kAccBytes + kWarpBufElems * 16);
-
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(&tmem_base_slot)));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    const int n = p.n;
-    const long long total = (long long)ga.ntempl * ga.n_inst;
-    long long g = (long long)blockIdx.x * 4 + warp;
-    const bool active = g < total;
-    if (!active) g = total - 1; /* idle warps shadow the last gate and write nothing: the CTA frees its TMEM together */
-    {
-        const int e = (int)(g / ga.ntempl), t = (int)(g - (long long)e * ga.ntempl);
-        GateT gt = ga.uni;
-        if (ga.tmpl) gt = ga.tmpl[t]; else { gt.in0 = (gt.in0 >= 0) ? t : -1; gt.in1 = (gt.in1 >= 0) ? t : -1; }
-        const size_t blk = (size_t)e * ga.inst_samples;
-        const int32_t *in0 = gt.in0 >= 0 ? baseA + (blk + gt.in0) * ga.stride : nullptr;
-        const int32_t *in1 = gt.in1 >= 0 ? baseB + (blk + gt.in1) * ga.stride : nullptr;
-        const int32_t c0 = gt.c0, c1 = gt.c1, cst = gt.cst_mu * p.mu;
-        for (int i = lane; i <= n; i += 32) {
-            int32_t v = (i == n) ? cst : 0;
-            if (in0) v += c0 * __ldg(in0 + i);
-            if (in1) v += c1 * __ldg(in1 + i);
-            abar[i] = (uint16_t)modswitch_2N(v);
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;");
-    const uint32_t taddr = tmem_base_slot + ((uint32_t)(warp * 32) << 16);
-    {
-        const int bbar = abar[n];
-        const int a = (2 * kN - bbar) & (2 * kN - 1), ar = a & (kN - 1);
-        const bool flip = a >= kN;
-        for (int j = lane; j < kN; j += 32) { acc[j] = 0; acc[kN + j] = ((j < ar) != flip) ? -p.mu : p.mu; }
-    }
-    __syncwarp();
-
-    const Tw16 w1 = tw16_pass1();
-    const Tw16 w2 = d_tw16[FOLD ? 0 : (lane & 15)]; /* FOLD: unused (the forward uses w2g, the inverse reloads from shared memory) */
-    const Tw16g w2g = d_tw16g[FOLD ? lane : 0];
-    const int Bgbit = p.Bgbit;
-    const uint32_t maskBg = (1u << Bgbit) - 1;
-    const int32_t halfBg = 1 << (Bgbit - 1);
-    uint32_t offset = 0;
-#pragma unroll
-    for (int i = 1; i <= L; i++) offset += (uint32_t)halfBg << (32 - i * Bgbit);
-    constexpr int kRowElems = 2 * kHalfN, kBkStride = 2 * L * kRowElems;
-
-    for (int i = 0; i < n; i++) {
-        const int a = abar[i];
-        const double2 *bk_r = bkw + (size_t)i * kBkStride + lane;
-        bool first = true;
-#pragma unroll 1
-        for (int q = 0; q < 2; q++) {
-            int32_t c[32];
-            rot_minus_one32(acc + q * kN, lane, a, c);
-#pragma unroll 1
-            for (int pp = 0; pp < L; pp++) {
-                const int shift = 32 - (pp + 1) * Bgbit;
-                double xr[16], xi[16];
-#pragma unroll
-                for (int m = 0; m < 16; m++) {
-                    xr[m] = digit_f64_magic(c[m], offset, shift, maskBg, halfBg);
-                    xi[m] = digit_f64_magic(c[16 + m], offset, shift, maskBg, halfBg);
-                }
-                /* forward transform */
-                pass16_fwd(xr, xi, w1);
-                __syncwarp();                      /* every lane has finished reading the buffer of the previous transform */
-                st16_pass1(buf, lane, xr, xi);
-                __syncwarp();
-                ld16_pass2(buf, lane, xr, xi);
-                if (FOLD) {
-                    /* select-free form: both lanes of a pair send registers 8..15, keep 0..7 and compute keep +- w recv;
-                     * the unit factors this leaves on the Lpar = 1 lanes are in the key layout (br_warp.h) */
-                    pass16_fwd_g(xr, xi, w2g);
-                    double sr[8], si[8], rr[8], ri[8], fzr[8], fzi[8];
-#pragma unroll
-                    for (int s8 = 0; s8 < 8; s8++) { sr[s8] = xr[8 + s8]; si[s8] = xi[8 + s8]; }
-                    warp_exchange8(sr, si, rr, ri);
-#pragma unroll
-                    for (int s8 = 0; s8 < 8; s8++) { fzr[s8] = s_finfr[s8][lane]; fzi[s8] = s_finfi[s8][lane]; }
-                    fin_fwd_apply_folded(xr, xi, rr, ri, fzr, fzi);
-                } else {
-                    pass16_fwd(xr, xi, w2);
-                    double sr[8], si[8], rr[8], ri[8], fzr[8], fzi[8];
-                    fin_fwd_send(xr, xi, lpar, sr, si);
-                    warp_exchange8(sr, si, rr, ri);
-#pragma unroll
-                    for (int s8 = 0; s8 < 8; s8++) { fzr[s8] = s_finr[s8][lane]; fzi[s8] = s_fini[s8][lane]; }
-                    fin_fwd_apply(xr, xi, lpar, rr, ri, fzr, fzi);
-                }
-                /* multiply-accumulate into TMEM: 8 slots of one output polynomial at a time; the BK_i values of chunk
-                 * c+1 are requested before chunk c is computed (the registers come from keeping the final-stage
-                 * twiddles in shared memory: 98.9 k -> 107.8 k gates/s).  Measured and rejected: 8 pipelined chunks of 4
-                 * slots (72 k: twice the tcgen05 round trips, spills); zeroing the accumulators with stores at the
-                 * start of a step instead of the `first` special case (89 k: 116 bytes of spills - the kernel sits at
-                 * 254 registers). */
-                if (!first) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                double2 bj[8];
-#pragma unroll
-                for (int r = 0; r < 8; r++) bj[r] = __ldg(bk_r + r * 32);
-#pragma unroll
-                for (int cidx = 0; cidx < 4; cidx++) {
-                    double sacc[16];
-                    const uint32_t tj = taddr + (uint32_t)(32 * cidx);
-                    if (!first) {
-                        IE_TMEM_LD16D(tj, sacc);
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < 16; r++) sacc[r] = 0.0;
-                    }
-                    const int sl = 8 * (cidx & 1); /* slots 8h..8h+7 of polynomial cidx >> 1 */
-#pragma unroll
-                    for (int r = 0; r < 8; r++) cmac(sacc[2 * r], sacc[2 * r + 1], xr[sl + r], xi[sl + r], bj[r].x, bj[r].y);
-                    if (cidx + 1 < 4) { /* the next chunk's BK_i values go into the registers just consumed, under the TMEM round trip */
-#pragma unroll
-                        for (int r = 0; r < 8; r++) bj[r] = ldg_pinned(bk_r + (8 * (cidx + 1) + r) * 32);
-                    }
-                    IE_TMEM_ST16D(tj, sacc);
-                }
-                first = false;
-                bk_r += kRowElems;
-            }
-        }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        /* inverse transforms and ACC update */
-#pragma unroll 1
-        for (int j = 0; j < 2; j++) {
-            double xr[16], xi[16];
-            {
-                double s0[16], s1[16];
-                IE_TMEM_LD16D(taddr + (uint32_t)(j * 64), s0);
-                IE_TMEM_LD16D(taddr + (uint32_t)(j * 64 + 32), s1);
-#pragma unroll
-                for (int r = 0; r < 8; r++) { xr[r] = s0[2 * r]; xi[r] = s0[2 * r + 1]; xr[8 + r] = s1[2 * r]; xi[8 + r] = s1[2 * r + 1]; }
-            }
-            {
-                double fzr[8], fzi[8];
-#pragma unroll
-                for (int s8 = 0; s8 < 8; s8++) { fzr[s8] = s_finr[s8][lane]; fzi[s8] = s_fini[s8][lane]; }
-                fin_inv_local(xr, xi, fzr, fzi);
-            }
-            {
-                double sr[8], si[8], rr[8], ri[8];
-                fin_inv_send(xr, xi, lpar, sr, si);
-                warp_exchange8(sr, si, rr, ri);
-                fin_inv_place(xr, xi, lpar, rr, ri);
-            }
-            if (FOLD) {
-                Tw16 wi;
-                double *dst = reinterpret_cast<double *>(&wi);
-#pragma unroll
-                for (int v = 0; v < 16; v++) dst[v] = s_tw2[v][lane & 15];
-                pass16_inv(xr, xi, wi);
-            } else {
-                pass16_inv(xr, xi, w2);
-            }
-            __syncwarp();
-            st16_ipass2(buf, lane, xr, xi);
-            __syncwarp();
-            ld16_ipass1(buf, lane, xr, xi);
-            pass16_inv(xr, xi, w1);
-            int32_t *accj = acc + j * kN;
-#pragma unroll
-            for (int m = 0; m < 16; m++) {
-                accj[lane + 32 * m] += round_to_torus(xr[m]);
-                accj[lane + 32 * m + 512] += round_to_torus(xi[m]);
-            }
-        }
-        __syncwarp();
-    }
-
-    if (active) {
-        int32_t *o = ext + (size_t)g * kExtStride;
-        for (int j = lane; j < kN; j += 32) o[j] = (j == 0) ? acc[0] : -acc[kN - j];
-        if (lane == 0) o[kN] = acc[kN];
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem_base_slot));
-}
-
-template <int L, bool FOLD>
-static cudaError_t launch_br_warp(const DevParams &p, const double2 *bkw, const GateAddr &ga, const int32_t *baseA,
-                                  const int32_t *baseB, int32_t *ext, long long count, cudaStream_t s)
-{
-    constexpr int smem = 4 * kWarpGateSmem;
-    cudaError_t e = cudaFuncSetAttribute(blind_rotate_warp_kernel<L, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    blind_rotate_warp_kernel<L, FOLD><<<(int)((count + 3) / 4), 128, smem, s>>>(p, bkw, ga, baseA, baseB, ext);
-    return cudaGetLastError();
+    /* 4. SampleExtract at index 0 */
+    int32_t *o = ext + (size_t)g * kExtStride;
+    for (int j = tid; j < kN; j += 64) o[j] = (j == 0) ? acc[0] : -acc[kN - j];
+    if (tid == 0) o[kN] = acc[kN];
 }
 
 /* ---- latency variant with two groups per gate: group q owns ACC polynomial q, runs its l forward transforms
@@ -821,8 +303,8 @@ static cudaError_t launch_br_warp(const DevParams &p, const double2 *bkw, const 
  * group per forward transform moved 192 KB per step and was LSU-bound at 72 %). */
 constexpr int pair_smem_bytes() { return kAccBytes + 2 * 2 * kBufBytes + 2 * kHalfN * 16 + kAbarBytes; }
 
-template <int L, int MINB = 2>
-__global__ void __launch_bounds__(128, MINB)
+template <int L>
+__global__ void __launch_bounds__(128, 2)
 blind_rotate_pair_kernel(DevParams p, const double2 *__restrict__ bkfft, GateAddr ga, const int32_t *__restrict__ baseA,
                          const int32_t *__restrict__ baseB, int32_t *__restrict__ ext)
 {
@@ -894,15 +376,9 @@ blind_rotate_pair_kernel(DevParams p, const double2 *__restrict__ bkfft, GateAdd
             /* the row's 16 KB of BK_i are requested before the transform: with one gate per SM nothing else hides
              * the L2 latency (the barriers inside the transform keep the compiler from sinking the loads) */
             double2 b0[8], b1[8];
-            if (MINB <= 2) {
 #pragma unroll
-                for (int r = 0; r < 8; r++) { b0[r] = __ldg(bk_mine + pp * kRowElems + r * 64); b1[r] = __ldg(bk_other + pp * kRowElems + r * 64); }
-            }
+            for (int r = 0; r < 8; r++) { b0[r] = __ldg(bk_mine + pp * kRowElems + r * 64); b1[r] = __ldg(bk_other + pp * kRowElems + r * 64); }
             fwd_transform(xr, xi, buf, tid, grp, w1, w2, w3);
-            if (MINB > 2) { /* three CTAs per SM leave 168 registers: no room to hold a row across the transform */
-#pragma unroll
-                for (int r = 0; r < 8; r++) { b0[r] = __ldg(bk_mine + pp * kRowElems + r * 64); b1[r] = __ldg(bk_other + pp * kRowElems + r * 64); }
-            }
 #pragma unroll
             for (int r = 0; r < 8; r++) {
                 cmac(mr[r], mi[r], xr[r], xi[r], b0[r].x, b0[r].y);
@@ -1140,16 +616,14 @@ static cudaError_t launch_br_cluster(const DevParams &p, const double2 *bkfft, c
                                      const int32_t *baseB, int32_t *ext, long long count, cudaStream_t s)
 {
     constexpr int smem = cluster_smem_bytes(L);
-    static const bool prof = getenv("IEACHE_CLUSTER_PROF") != nullptr; /* developer aid: per-phase cycle counts of cluster 0 */
-    if (prof) {
-        cudaError_t e = cudaFuncSetAttribute(blind_rotate_cluster_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        blind_rotate_cluster_kernel<L, true><<<(int)count * 2, 64 * L, smem, s>>>(p, bkfft, ga, baseA, baseB, ext);
-        return cudaGetLastError();
-    }
-    cudaError_t e = cudaFuncSetAttribute(blind_rotate_cluster_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+#ifdef IEACHE_CLUSTER_PROF /* developer build: per-phase cycle counts of cluster 0 on stdout */
+    constexpr bool prof = true;
+#else
+    constexpr bool prof = false;
+#endif
+    cudaError_t e = cudaFuncSetAttribute(blind_rotate_cluster_kernel<L, prof>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    blind_rotate_cluster_kernel<L><<<(int)count * 2, 64 * L, smem, s>>>(p, bkfft, ga, baseA, baseB, ext);
+    blind_rotate_cluster_kernel<L, prof><<<(int)count * 2, 64 * L, smem, s>>>(p, bkfft, ga, baseA, baseB, ext);
     return cudaGetLastError();
 }
 
@@ -1158,141 +632,65 @@ static cudaError_t launch_br_pair(const DevParams &p, const double2 *bkfft, cons
                                   const int32_t *baseB, int32_t *ext, long long count, cudaStream_t s)
 {
     constexpr int smem = pair_smem_bytes();
-    static const bool three = getenv("IEACHE_PAIR_3CTA") != nullptr; /* experiment: 3 CTAs per SM at 168 registers */
-    if (three) {
-        cudaError_t e = cudaFuncSetAttribute(blind_rotate_pair_kernel<L, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        blind_rotate_pair_kernel<L, 3><<<(int)count, 128, smem, s>>>(p, bkfft, ga, baseA, baseB, ext);
-        return cudaGetLastError();
-    }
     cudaError_t e = cudaFuncSetAttribute(blind_rotate_pair_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     blind_rotate_pair_kernel<L><<<(int)count, 128, smem, s>>>(p, bkfft, ga, baseA, baseB, ext);
     return cudaGetLastError();
 }
 
-/* launches of at most this many gates use the latency kernel: 3 waves of 148 one-gate CTAs take about as
- * long as one wave of the throughput kernel (4 gates per SM) */
-static long long g_wide_max = [] { const char *e = getenv("IEACHE_WIDE_MAX"); return e ? atoll(e) : 296LL; }();
-void set_wide_max(long long v) { g_wide_max = v; }
-long long get_wide_max() { return g_wide_max; }
-/* launches of at most this many gates use the 2-CTA-cluster kernel: 74 pairs of SMs run in one wave */
-static long long g_cluster_max = [] { const char *e = getenv("IEACHE_CLUSTER_MAX"); return e ? atoll(e) : 74LL; }();
-void set_cluster_max(long long v) { g_cluster_max = v; }
-long long get_cluster_max() { return g_cluster_max; }
-
-/* launch configuration: IEACHE_BR_VARIANT selects among the compiled variants (tuning aid) */
-static int g_br_variant = -1;
-static int br_variant()
+template <int L, int ROLL, bool ACCREG>
+static cudaError_t launch_br_group(const DevParams &p, const double2 *bkfft, const GateAddr &ga, const int32_t *baseA,
+                                   const int32_t *baseB, int32_t *ext, long long count, cudaStream_t s)
 {
-    if (g_br_variant < 0) { const char *e = getenv("IEACHE_BR_VARIANT"); g_br_variant = e ? atoi(e) : 41; }
-    return g_br_variant;
-}
-int set_throughput_variant(int v) { const int old = br_variant(); if (v >= 0) g_br_variant = v; return old; }
-int blind_rotate_groups_per_cta() { const int v = br_variant(); return (v == 4 || v == 11 || v == 13 || v == 31 || v == 34) ? 4 : ((v == 0 || v == 1 || v == 3 || v == 5 || v == 6 || v == 12 || v == 30 || v == 32 || v == 33) ? 2 : 1); }
-int blind_rotate_smem_bytes(int groups) { return groups * kGroupSmem; }
-
-template <int L, int G, int MINB, int ROLL, int NOBK = 0, bool LOCK = false, bool SPREAD = false, bool ACCREG = false>
-static cudaError_t launch_br_variant(const DevParams &p, const double2 *bkfft, const GateAddr &ga, const int32_t *baseA,
-                                     const int32_t *baseB, int32_t *ext, long long count, cudaStream_t s)
-{
-    const int smem = G * kGroupSmem + (NOBK == 2 ? 2 * kHalfN * 16 : 0);
-    const int grid = (int)((count + G - 1) / G);
-    cudaError_t e = cudaFuncSetAttribute(blind_rotate_kernel<L, G, MINB, ROLL, NOBK, LOCK, SPREAD, ACCREG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(blind_rotate_kernel<L, ROLL, ACCREG>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGroupSmem);
     if (e != cudaSuccess) return e;
-    static const int stagger = [] { const char *e = getenv("IEACHE_BR_STAGGER"); return e ? atoi(e) : 0; }();
-    static const int sms = [] { int d = 0, v = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
-    blind_rotate_kernel<L, G, MINB, ROLL, NOBK, LOCK, SPREAD, ACCREG><<<grid, 64 * G, smem, s>>>(p, bkfft, ga, baseA, baseB, ext, stagger, sms);
+    blind_rotate_kernel<L, ROLL, ACCREG><<<(int)count, 64, kGroupSmem, s>>>(p, bkfft, ga, baseA, baseB, ext);
     return cudaGetLastError();
 }
 
-int blind_rotate_warp_layout(long long count) /* 0 = not needed, 1 = plain warp layout, 2 = folded (variant 61) */
+/* Which kernel a launch of `count` gates uses (measured table in DESIGN.md 4):
+ *   <= cluster_max            one gate on a 2-CTA cluster (1.6 ms per gate, 74 clusters per wave)
+ *   <= pair_max               one gate per CTA, two groups (2.1 ms, 148-gate steps)
+ *   >= w12_min                persistent kernel, 12 gates per SM (1 776-gate rounds)
+ *   between                   group kernel (592-gate waves), or the two-group kernel when the group kernel's last
+ *                             wave would be less than 90 % full */
+int pick_blind_rotate(const LaunchPolicy &pol, long long count)
 {
-    if (count <= 0) return 0;
-    return br_variant() == 60 ? 1 : (br_variant() == 61 ? 2 : (br_variant() == 70 ? 3 : 0));
+    if (count <= pol.cluster_max && count <= pol.pair_max) return BR_CLUSTER;
+    if (count <= pol.pair_max) return BR_PAIR;
+    if (pol.throughput == BR_GROUP || pol.throughput == BR_W12) return pol.throughput;
+    if (count >= pol.w12_min) return BR_W12;
+    if (pol.pair_max > 0) {
+        const long long slots = 4LL * pol.sms, waves = (count + slots - 1) / slots;
+        if (count * 10 < waves * slots * 9) return BR_PAIR;
+    }
+    return BR_GROUP;
 }
 
-cudaError_t launch_blind_rotate(const DevParams &p, const double2 *bkfft, const double2 *bkfft_w, const GateAddr &ga, const int32_t *baseA,
-                                const int32_t *baseB, int32_t *ext, int ext_base, cudaStream_t s)
+cudaError_t launch_blind_rotate(const DevParams &p, const LaunchPolicy &pol, const double2 *bkfft, const double2 *bkfft_w, const GateAddr &ga,
+                                const int32_t *baseA, const int32_t *baseB, int32_t *ext, int ext_base, cudaStream_t s)
 {
     const long long count = (long long)ga.ntempl * ga.n_inst;
     if (count <= 0) return cudaSuccess;
+    if (p.l != 2 && p.l != 3) return cudaErrorInvalidValue;
     ext += (size_t)ext_base * kExtStride;
-    /* narrow launches (a circuit level of a few expressions): per-gate latency is what matters */
-    if (count <= g_cluster_max && count <= g_wide_max) {
-        if (p.l == 3) return launch_br_cluster<3>(p, bkfft, ga, baseA, baseB, ext, count, s);
-        if (p.l == 2) return launch_br_cluster<2>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    }
-    /* The throughput kernel holds 4 gates per SM, so its time moves in steps of 4 x SMs gates (592: 5.8 ms, 720:
-     * 9.3 ms); the two-group kernel holds 2 gates per SM at 97 % of the throughput kernel's full-wave rate and
-     * finer steps (720 gates: 7.4 ms).  Launches that would leave more than 10 % of the throughput kernel's last
-     * wave empty therefore also use it (measured table in DESIGN.md 4). */
-    bool two_group = count <= g_wide_max;
-    if (!two_group && g_wide_max > 0) {
-        static const long long slots = [] { int d = 0, sms = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d); return 4LL * sms; }();
-        const long long waves = (count + slots - 1) / slots;
-        two_group = count * 10 < waves * slots * 9;
-    }
-    if (two_group) {
-        if (p.l == 3) return launch_br_pair<3>(p, bkfft, ga, baseA, baseB, ext, count, s);
-        if (p.l == 2) return launch_br_pair<2>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    }
-    if (bkfft_w && br_variant() == 70) return launch_blind_rotate_w12(p, bkfft_w, ga, baseA, baseB, ext, count, s);
-    if (bkfft_w && br_variant() == 60) {
-        if (p.l == 3) return launch_br_warp<3, false>(p, bkfft_w, ga, baseA, baseB, ext, count, s);
-        if (p.l == 2) return launch_br_warp<2, false>(p, bkfft_w, ga, baseA, baseB, ext, count, s);
-    }
-    if (bkfft_w && br_variant() == 61) {
-        if (p.l == 3) return launch_br_warp<3, true>(p, bkfft_w, ga, baseA, baseB, ext, count, s);
-        if (p.l == 2) return launch_br_warp<2, true>(p, bkfft_w, ga, baseA, baseB, ext, count, s);
-    }
-    if (p.l == 2) return launch_br_variant<2, 1, 4, 2>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    if (p.l != 3) return cudaErrorInvalidValue;
-    switch (br_variant()) {
-    case 52: return launch_br_tmem<3, 2>(p, bkfft, ga, baseA, baseB, ext, count, s); /* accumulators in TMEM, 2 gates per group */
-    case 51: return launch_br_tmem<3, 1>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 55: return launch_br_tmem<3, 1, 5>(p, bkfft, ga, baseA, baseB, ext, count, s); /* 5 / 6 CTAs per SM: the registers the */
-    case 56: return launch_br_tmem<3, 1, 6>(p, bkfft, ga, baseA, baseB, ext, count, s); /* accumulators no longer occupy      */
-    case 0: return launch_br_variant<3, 2, 2, 0>(p, bkfft, ga, baseA, baseB, ext, count, s); /* round-1 first version */
-    case 2: return launch_br_variant<3, 1, 6, 1>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 3: return launch_br_variant<3, 2, 2, 1>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 4: return launch_br_variant<3, 4, 1, 1>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 5: return launch_br_variant<3, 2, 4, 1>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 6: return launch_br_variant<3, 2, 3, 0>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 8: return launch_br_variant<3, 1, 5, 0>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 9: return launch_br_variant<3, 1, 6, 0>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 10: return launch_br_variant<3, 1, 5, 1>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 21: return launch_br_variant<3, 1, 6, 2>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 22: return launch_br_variant<3, 1, 6, 3>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 24: return launch_br_variant<3, 1, 4, 3>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    /* SPREAD: lanes of 2 / 4 gates interleaved in every warp (shared BK_i wavefronts) */
-    case 30: return launch_br_variant<3, 2, 2, 2, false, true, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 31: return launch_br_variant<3, 4, 1, 2, false, true, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 32: return launch_br_variant<3, 2, 3, 2, false, true, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 33: return launch_br_variant<3, 2, 2, 0, false, true, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 34: return launch_br_variant<3, 4, 1, 0, false, true, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 11: return launch_br_variant<3, 4, 1, 0, false, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 12: return launch_br_variant<3, 2, 2, 0, false, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 13: return launch_br_variant<3, 4, 1, 0, false, false>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    /* timing experiments only (wrong results): no BK loads */
-    case 107: return launch_br_variant<3, 1, 4, 0, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 40: return launch_br_variant<3, 1, 4, 2, 0, false, false, true>(p, bkfft, ga, baseA, baseB, ext, count, s); /* ACC in registers */
-    case 41: return launch_br_variant<3, 1, 4, 0, 0, false, false, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 307: return launch_br_variant<3, 1, 4, 0, 3, false, false, true>(p, bkfft, ga, baseA, baseB, ext, count, s); /* -19 % FP64, same LSU */
-    case 207: return launch_br_variant<3, 1, 4, 2, 2>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 208: return launch_br_variant<3, 1, 5, 2, 2>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 109: return launch_br_variant<3, 1, 6, 0, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 102: return launch_br_variant<3, 1, 6, 1, true>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 1: return launch_br_variant<3, 2, 3, 1>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 7: return launch_br_variant<3, 1, 4, 0>(p, bkfft, ga, baseA, baseB, ext, count, s);
-    case 23: return launch_br_variant<3, 1, 4, 2>(p, bkfft, ga, baseA, baseB, ext, count, s); /* as fast as the fully unrolled body (7) at half the code size */
-    default: return launch_br_variant<3, 1, 4, 0, 0, false, false, true>(p, bkfft, ga, baseA, baseB, ext, count, s); /* 41: ACC coefficients in registers, +1.2 % over 23 */
+    switch (pick_blind_rotate(pol, count)) {
+    case BR_CLUSTER:
+        return p.l == 3 ? launch_br_cluster<3>(p, bkfft, ga, baseA, baseB, ext, count, s) : launch_br_cluster<2>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case BR_PAIR:
+        return p.l == 3 ? launch_br_pair<3>(p, bkfft, ga, baseA, baseB, ext, count, s) : launch_br_pair<2>(p, bkfft, ga, baseA, baseB, ext, count, s);
+    case BR_W12:
+        if (!bkfft_w) return cudaErrorInvalidValue; /* the caller lays the key out when pick_blind_rotate says BR_W12 */
+        return launch_blind_rotate_w12(p, bkfft_w, ga, baseA, baseB, ext, count, pol.sms, s);
+    default:
+        /* l = 3: unrolled step body with the ACC coefficients in registers; l = 2 keeps the rolled form it was validated in */
+        return p.l == 3 ? launch_br_group<3, 0, true>(p, bkfft, ga, baseA, baseB, ext, count, s)
+                        : launch_br_group<2, 2, false>(p, bkfft, ga, baseA, baseB, ext, count, s);
     }
 }
 
 /* ------------------------------------------------------------------ key switch */
 constexpr int kKsThreads = 160; /* 158 int4 lanes cover a 632-word row */
-constexpr int kKsMaxRows = 1024 * 16;
 
 __global__ void __launch_bounds__(kKsThreads)
 keyswitch_kernel(DevParams p, const int32_t *__restrict__ ksk, GateAddr ga, int32_t *__restrict__ out_base,
@@ -1451,7 +849,8 @@ __global__ void __launch_bounds__(kKsStageThreads, 1)
 keyswitch_staged_kernel(DevParams p, const int32_t *__restrict__ ksk, GateAddr ga, int32_t *__restrict__ out_base,
                         const int32_t *__restrict__ ext, int pair_offset, int32_t cst_post)
 {
-    extern __shared__ __align__(128) unsigned char ks_smem[];
+    extern __shared__ __align__(128) unsigned char ks_stage_smem[];
+    unsigned char *ks_smem = ks_stage_smem;
     int4 *stage = reinterpret_cast<int4 *>(ks_smem);                                   /* [kKsRing][block rows][158] */
     int32_t *u_all = reinterpret_cast<int32_t *>(ks_smem + kKsRing * kKsStageBlockBytes);    /* [kKsGates][1028] */
     uint64_t *mbar = reinterpret_cast<uint64_t *>(ks_smem + kKsStageSmem - 64);        /* full[kKsRing], empty[kKsRing] */
@@ -1554,44 +953,45 @@ keyswitch_staged_kernel(DevParams p, const int32_t *__restrict__ ksk, GateAddr g
     if (third) put(tid + 128, a2);
 }
 
-/* launches of at least this many gates use the staged kernel: a CTA needs ~0.96 ms for its 12 gates whatever the
- * launch size, the gather kernel ~0.95 us per gate, so they cross near 1000 gates */
-static long long g_ks_staged_min = [] { const char *e = getenv("IEACHE_KS_STAGED_MIN"); return e ? atoll(e) : 1000LL; }();
-void set_ks_staged_min(long long v) { g_ks_staged_min = v; }
-long long get_ks_staged_min() { return g_ks_staged_min; }
+/* Which key-switch kernel: launches of at most pair_max gates use the 8-CTA cluster kernel; launches of at least
+ * ks_staged_min gates the staged kernel (a CTA needs ~0.96 ms for its 12 gates whatever the launch size, the gather
+ * kernel ~0.95 us per gate, so they cross near 1000 gates) */
+int pick_keyswitch(const LaunchPolicy &pol, const DevParams &p, long long count)
+{
+    if (count <= pol.pair_max && p.ks_t <= 16) return KS_CLUSTER;
+    const int block_rows = p.ks_t * ((1 << p.ks_basebit) - 1);
+    if (block_rows <= 24 && count >= pol.ks_staged_min) return KS_STAGED;
+    return KS_GATHER;
+}
 
-cudaError_t launch_keyswitch(const DevParams &p, const int32_t *ksk, const GateAddr &ga, int32_t *out_base,
+cudaError_t launch_keyswitch(const DevParams &p, const LaunchPolicy &pol, const int32_t *ksk, const GateAddr &ga, int32_t *out_base,
                              const int32_t *ext, int pair_offset, int32_t cst_post, cudaStream_t s)
 {
     const long long count = (long long)ga.ntempl * ga.n_inst;
     if (count <= 0) return cudaSuccess;
     const int smem = kN * p.ks_t * 4;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(keyswitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
     if (smem > 64 * 1024) return cudaErrorInvalidValue;
-    if (count <= g_wide_max && p.ks_t <= 16) {
+    /* function attributes are per device: set on every launch (as the blind-rotation launchers do) so that a process
+     * with contexts on several GPUs gets the opt-in on each of them */
+    switch (pick_keyswitch(pol, p, count)) {
+    case KS_CLUSTER:
         keyswitch_cluster_kernel<<<(unsigned)count * kKsCluster, kKsThreads, 0, s>>>(p, ksk, ga, out_base, ext, pair_offset, cst_post);
         return cudaGetLastError();
-    }
-    /* wide launches: row blocks staged once per kKsGates gates */
-    const int block_rows = p.ks_t * ((1 << p.ks_basebit) - 1);
-    if (block_rows <= kKsMaxBlockRows && count >= g_ks_staged_min) {
-        static bool attr2 = false;
-        if (!attr2) {
-            cudaError_t e = cudaFuncSetAttribute(keyswitch_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKsStageSmem);
-            if (e != cudaSuccess) return e;
-            attr2 = true;
-        }
+    case KS_STAGED: {
+        static_assert(kKsMaxBlockRows == 24, "pick_keyswitch assumes 24-row blocks");
+        cudaError_t e = cudaFuncSetAttribute(keyswitch_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKsStageSmem);
+        if (e != cudaSuccess) return e;
         const unsigned grid = (unsigned)((count + kKsGates - 1) / kKsGates);
         keyswitch_staged_kernel<<<grid, kKsStageThreads, kKsStageSmem, s>>>(p, ksk, ga, out_base, ext, pair_offset, cst_post);
         return cudaGetLastError();
     }
-    keyswitch_kernel<<<(unsigned)count, kKsThreads, smem, s>>>(p, ksk, ga, out_base, ext, pair_offset, cst_post);
-    return cudaGetLastError();
+    default: {
+        cudaError_t e = cudaFuncSetAttribute(keyswitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e != cudaSuccess) return e;
+        keyswitch_kernel<<<(unsigned)count, kKsThreads, smem, s>>>(p, ksk, ga, out_base, ext, pair_offset, cst_post);
+        return cudaGetLastError();
+    }
+    }
 }
 
 /* ------------------------------------------------------------------ small helpers */

@@ -47,28 +47,40 @@ struct DevParams {
     int32_t mu;           /* bootstrap message, 2^29 */
 };
 
-/* one-time: upload the pass-2 / pass-3 twiddle tables to the current device */
+/* Launch policy of one context: which kernel shape a launch of a given size uses.  Held by ieache_ctx (no process-wide
+ * state), initialised from the defaults below and from IEACHE_* environment overrides at context creation. */
+enum { BR_CLUSTER = 1, BR_PAIR = 2, BR_GROUP = 41, BR_W12 = 70 };
+enum { KS_CLUSTER = 1, KS_GATHER = 2, KS_STAGED = 3 };
+struct LaunchPolicy {
+    long long cluster_max = 74;     /* <= : one gate on a 2-CTA cluster (74 clusters in one wave) */
+    long long pair_max = 296;       /* <= : one gate per CTA, two groups; also the 8-CTA-cluster key switch */
+    long long w12_min = 900;        /* >= : persistent 12-warp kernel (1 776 gates per round) */
+    long long ks_staged_min = 1000; /* >= : staged key switch */
+    int throughput = 0;             /* 0 = by size; BR_GROUP / BR_W12 = that kernel for every launch above pair_max */
+    int sms = 148;
+};
+int pick_blind_rotate(const LaunchPolicy &pol, long long count);
+int pick_keyswitch(const LaunchPolicy &pol, const DevParams &p, long long count);
+
+/* one-time: upload the twiddle tables to the current device */
 cudaError_t upload_twiddles();
 
 /* key load: coefficient-domain BK polys int32[npoly][1024] -> bkfft layout.
  * poly index q = ((i*kpl + r)*2 + j). */
 cudaError_t launch_bk_fft(const int32_t *bk_coef, double2 *bkfft, int npoly, cudaStream_t s);
 
-/* blind rotation + sample extraction of ntempl*n_inst gates -> ext[ext_base + g][1028] */
-/* bkfft_w: the same key in the warp-per-gate layout [row][poly][slot 16][lane 32] (launch_bk_relayout_warp), or nullptr */
-cudaError_t launch_blind_rotate(const DevParams &p, const double2 *bkfft, const double2 *bkfft_w, const GateAddr &ga, const int32_t *baseA,
-                                const int32_t *baseB, int32_t *ext, int ext_base, cudaStream_t s);
-int blind_rotate_warp_layout(long long count); /* which layout the selected variant reads: 0 none, 1 plain, 2 folded */
-/* which compiled variant of the throughput blind rotation wide launches use (41 = default register kernel, 60 = one
- * warp per gate with TMEM accumulators, 51/52/55/56 = TMEM accumulators with 64-thread groups, ...); returns the old one */
-int set_throughput_variant(int v);
-/* br_w12.cu: persistent warp-per-gate blind rotation (12 gates per SM), reads the warp-layout key */
+/* blind rotation + sample extraction of ntempl*n_inst gates -> ext[ext_base + g][1028].
+ * bkfft_w: the same key in the persistent kernel's layout [row][poly][slot 16][lane 32] (launch_bk_relayout_w12);
+ * required when pick_blind_rotate(pol, count) == BR_W12 */
+cudaError_t launch_blind_rotate(const DevParams &p, const LaunchPolicy &pol, const double2 *bkfft, const double2 *bkfft_w, const GateAddr &ga,
+                                const int32_t *baseA, const int32_t *baseB, int32_t *ext, int ext_base, cudaStream_t s);
+/* br_w12.cu: persistent warp-per-gate blind rotation (12 gates per SM) */
 cudaError_t upload_twiddles_w12();
 cudaError_t launch_blind_rotate_w12(const DevParams &p, const double2 *bkfft_w, const GateAddr &ga, const int32_t *baseA,
-                                    const int32_t *baseB, int32_t *ext, long long count, cudaStream_t s);
-cudaError_t launch_bk_relayout_warp(const double2 *bkfft, double2 *bkfft_w, int npoly, int folded, cudaStream_t s);
+                                    const int32_t *baseB, int32_t *ext, long long count, int sms, cudaStream_t s);
+cudaError_t launch_bk_relayout_w12(const double2 *bkfft, double2 *bkfft_w, int npoly, cudaStream_t s);
 /* key switch of ext[g] (+ ext[g + pair_offset] if pair_offset > 0) + (0, cst_post) into sample out of out_base */
-cudaError_t launch_keyswitch(const DevParams &p, const int32_t *ksk, const GateAddr &ga, int32_t *out_base,
+cudaError_t launch_keyswitch(const DevParams &p, const LaunchPolicy &pol, const int32_t *ksk, const GateAddr &ga, int32_t *out_base,
                              const int32_t *ext, int pair_offset, int32_t cst_post, cudaStream_t s);
 
 /* free linear ops on whole arrays (bootsNOT / bootsCOPY / bootsCONSTANT) */
@@ -85,19 +97,6 @@ cudaError_t launch_circuit_gather_outputs(int32_t *outputs, const int32_t *wires
 
 /* dense FP64 FMA microbenchmark (best of 3), TFLOP/s */
 cudaError_t launch_fp64_peak(cudaStream_t s, double *tflops);
-
-/* launches with <= wide_max gates use the two-group latency kernel (one gate per CTA, one group per ACC polynomial) */
-void set_wide_max(long long v);
-long long get_wide_max();
-/* launches with <= cluster_max gates (and <= wide_max) use the 2-CTA-cluster latency kernel (one gate on two SMs) */
-void set_cluster_max(long long v);
-long long get_cluster_max();
-/* key-switch launches with >= ks_staged_min gates use the staged kernel (row blocks shared by 12 gates per CTA) */
-void set_ks_staged_min(long long v);
-long long get_ks_staged_min();
-
-int blind_rotate_smem_bytes(int groups);
-int blind_rotate_groups_per_cta();
 
 } // namespace ieache
 #endif

@@ -7,48 +7,57 @@
  *   Output/verif.c:93       bootsSymDecrypt                              -> phase_kernel
  * They also give bench.py a synthetic key and synthetic ciphertexts without touching the oracle.
  *
- * Randomness: counter-based (splitmix64 finaliser over (seed, stream, index)); uniform torus
- * values and Box-Muller Gaussians.  libtfhe's own generator (std::default_random_engine behind
- * tfhe_random_generator_setSeed, Keygen/keygen.c:30-36) is not reproducible across standard
- * libraries, so no attempt is made to reproduce its streams (SURVEY.md App. A "Randomness").
+ * Randomness: counter-mode ChaCha20 (csprng.h) under two independent 256-bit keys per key set — `secret` for the key
+ * bits and every noise term, `mask` for the published uniform masks — taken from the operating system unless a
+ * seed is given (tests only).  Box-Muller Gaussians.  libtfhe's own generator (std::default_random_engine behind
+ * tfhe_random_generator_setSeed, Keygen/keygen.c:30-36) is not reproducible across standard libraries, so no
+ * attempt is made to reproduce its streams (SURVEY.md App. A "Randomness").
  */
 #include "kernels.h"
 #include "br_core.h"
 #include "keygen.h"
+#include "csprng.h"
+
+#include <sys/random.h>
+#include <string.h>
 
 namespace ieache {
 
 /* defined in kernels.cu: device addresses of the pass-2 / pass-3 twiddle tables */
 cudaError_t twiddle_ptrs(const Tw **tw2, const Tw **tw3);
 
-__host__ __device__ inline uint64_t mix64(uint64_t z)
+int rng_keys_from_os(RngKeys &out)
 {
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
+    unsigned char *p = reinterpret_cast<unsigned char *>(&out);
+    size_t got = 0;
+    while (got < sizeof(out)) {
+        const ssize_t r = getrandom(p + got, sizeof(out) - got, 0);
+        if (r <= 0) return -1;
+        got += (size_t)r;
+    }
+    return 0;
 }
-__host__ __device__ inline uint64_t rnd64(uint64_t seed, uint64_t stream, uint64_t idx)
+void rng_keys_from_seed(uint64_t seed, RngKeys &out)
 {
-    return mix64(mix64(seed + 0x9E3779B97F4A7C15ull * (stream + 1)) ^ (idx * 0xD1342543DE82EF95ull + 0x2545F4914F6CDD1Dull));
-}
-__device__ inline int32_t rnd_torus(uint64_t seed, uint64_t stream, uint64_t idx) { return (int32_t)(uint32_t)(rnd64(seed, stream, idx) >> 32); }
-/* Gaussian of standard deviation sigma (torus units) as a Torus32 (libtfhe gaussian32 / dtot32) */
-__device__ inline int32_t rnd_gauss_torus(uint64_t seed, uint64_t stream, uint64_t idx, double sigma)
-{
-    const uint64_t r = rnd64(seed, stream, idx);
-    const double u1 = ((double)(uint32_t)(r >> 32) + 1.0) * (1.0 / 4294967296.0);
-    const double u2 = (double)(uint32_t)r * (1.0 / 4294967296.0);
-    const double g = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2) * sigma;
-    return (int32_t)(int64_t)((g - floor(g + 0.5)) * 4294967296.0);
-}
-
-void host_random_bits(uint64_t seed, uint64_t stream, int32_t *out, int count)
-{
-    for (int i = 0; i < count; i++) out[i] = (int32_t)(rnd64(seed, stream, (uint64_t)i) >> 63);
+    /* the seed keys a ChaCha20 stream whose first two blocks become the two keys: reproducible, and no stronger than
+     * the 64-bit seed — tests only */
+    RngKey base{};
+    base.k[0] = (uint32_t)seed; base.k[1] = (uint32_t)(seed >> 32); base.k[2] = 0x69656163u; base.k[3] = 0x68655f62u; /* "ieache_b" */
+    uint32_t blk[16];
+    chacha20_block(base, 0, RNG_DERIVE, blk);
+    memcpy(out.secret.k, blk, 32);
+    chacha20_block(base, 1, RNG_DERIVE, blk);
+    memcpy(out.mask.k, blk, 32);
 }
 
-enum : uint64_t { STREAM_LWE_KEY = 1, STREAM_TLWE_KEY = 2, STREAM_BK_A = 3, STREAM_BK_E = 4, STREAM_KS_A = 5, STREAM_KS_E = 6,
-                  STREAM_ENC_A = 7, STREAM_ENC_E = 8 };
+void host_key_bits(const RngKey &secret, uint64_t stream, int32_t *out, int count)
+{
+    uint32_t blk[16];
+    for (int i = 0; i < count; i++) {
+        if ((i & 511) == 0) chacha20_block(secret, (uint64_t)(i >> 9), stream, blk);
+        out[i] = (int32_t)((blk[(i & 511) >> 5] >> (i & 31)) & 1u);
+    }
+}
 
 __device__ __forceinline__ void gsync() { __syncthreads(); }
 
@@ -83,7 +92,7 @@ __global__ void __launch_bounds__(64) keygen_sfft_kernel(const int32_t *__restri
 /* one CTA per TGSW row (i, r): TLWE encryption of 0 plus s_i * h_p on the diagonal, written
  * straight into the transform-domain layout (and optionally in coefficient form for export) */
 __global__ void __launch_bounds__(64)
-keygen_bk_kernel(uint64_t seed, int l, int Bgbit, double bk_stdev, const int32_t *__restrict__ lwe_key,
+keygen_bk_kernel(RngKeys keys, int l, int Bgbit, double bk_stdev, const int32_t *__restrict__ lwe_key,
                  const double2 *__restrict__ shat, double2 *__restrict__ bkfft, int32_t *__restrict__ bk_coef,
                  const Tw *__restrict__ d_tw2, const Tw *__restrict__ d_tw3)
 {
@@ -94,10 +103,11 @@ keygen_bk_kernel(uint64_t seed, int l, int Bgbit, double bk_stdev, const int32_t
     const int32_t msg = lwe_key[i] * (int32_t)(1u << (32 - (pp + 1) * Bgbit));
     int32_t a[16];
     double xr[8], xi[8];
+    {   /* the thread's 16 mask coefficients are the 16 words of one key-stream block */
+        uint32_t blk[16];
+        chacha20_block(keys.mask, (uint64_t)row * 64 + tid, RNG_BK_MASK, blk);
 #pragma unroll
-    for (int h = 0; h < 16; h++) {
-        const int j = tid + 64 * (h & 7) + 512 * (h >> 3);
-        a[h] = rnd_torus(seed, STREAM_BK_A, (uint64_t)row * kN + j);
+        for (int h = 0; h < 16; h++) a[h] = (int32_t)blk[h];
     }
 #pragma unroll
     for (int m = 0; m < 8; m++) { xr[m] = (double)a[m]; xi[m] = (double)a[8 + m]; }
@@ -112,11 +122,15 @@ keygen_bk_kernel(uint64_t seed, int l, int Bgbit, double bk_stdev, const int32_t
     }
     inv64(pr, pi, buf, tid, w1, w2, w3);
     int32_t b[16];
+    {
+        uint32_t n0[16], n1[16]; /* 16 Gaussians = 32 words = two blocks of the secret stream */
+        chacha20_block(keys.secret, ((uint64_t)row * 64 + tid) * 2, RNG_BK_NOISE, n0);
+        chacha20_block(keys.secret, ((uint64_t)row * 64 + tid) * 2 + 1, RNG_BK_NOISE, n1);
 #pragma unroll
-    for (int h = 0; h < 16; h++) {
-        const int j = tid + 64 * (h & 7) + 512 * (h >> 3);
-        const double v = ((h < 8) ? pr[h & 7] : pi[h & 7]) * (1.0 / 512.0);
-        b[h] = round_to_torus(v) + rnd_gauss_torus(seed, STREAM_BK_E, (uint64_t)row * kN + j, bk_stdev);
+        for (int h = 0; h < 16; h++) {
+            const double v = ((h < 8) ? pr[h & 7] : pi[h & 7]) * (1.0 / 512.0);
+            b[h] = round_to_torus(v) + gauss_torus(h < 8 ? n0[2 * h] : n1[2 * (h - 8)], h < 8 ? n0[2 * h + 1] : n1[2 * (h - 8) + 1], bk_stdev);
+        }
     }
     if (tid == 0) { if (q == 0) a[0] += msg; else b[0] += msg; }
     if (bk_coef) {
@@ -140,7 +154,7 @@ keygen_bk_kernel(uint64_t seed, int l, int Bgbit, double bk_stdev, const int32_t
 }
 
 /* one warp per key-switch row (i, j, d), d = 1..base-1 */
-__global__ void keygen_ksk_kernel(uint64_t seed, int n, int t, int basebit, double ks_stdev, const int32_t *__restrict__ lwe_key,
+__global__ void keygen_ksk_kernel(RngKeys keys, int n, int t, int basebit, double ks_stdev, const int32_t *__restrict__ lwe_key,
                                   const int32_t *__restrict__ tlwe_key, int32_t *__restrict__ ksk, int32_t *__restrict__ ksk_export,
                                   int rows)
 {
@@ -151,23 +165,26 @@ __global__ void keygen_ksk_kernel(uint64_t seed, int n, int t, int basebit, doub
     int32_t *o = ksk + (size_t)row * kLweStride;
     int32_t *e = ksk_export ? ksk_export + ((size_t)ij * (basem1 + 1) + d) * (n + 1) : nullptr;
     int32_t acc = 0;
-    for (int q = lane; q < kLweStride; q += 32) {
+    uint32_t blk[16];
+    for (int q = lane, k = 0; q < kLweStride; q += 32, k++) { /* word k of the lane: block k / 16 of its (row, lane) counter pair */
+        if ((k & 15) == 0) chacha20_block(keys.mask, ((uint64_t)row * 32 + lane) * 2 + (k >> 4), RNG_KS_MASK, blk);
         int32_t v = 0;
-        if (q < n) { v = rnd_torus(seed, STREAM_KS_A, (uint64_t)row * 1024 + q); acc += v * lwe_key[q]; }
+        if (q < n) { v = (int32_t)blk[k & 15]; acc += v * lwe_key[q]; }
         if (q != n) { o[q] = v; if (e && q < n) e[q] = v; }
     }
 #pragma unroll
     for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
     if (lane == 0) {
+        chacha20_block(keys.secret, (uint64_t)row, RNG_KS_NOISE, blk);
         const int32_t msg = (int32_t)((uint32_t)(d * tlwe_key[i]) << (32 - (j + 1) * basebit));
-        const int32_t b = acc + msg + rnd_gauss_torus(seed, STREAM_KS_E, row, ks_stdev);
+        const int32_t b = acc + msg + gauss_torus(blk[0], blk[1], ks_stdev);
         o[n] = b;
         if (e) e[n] = b;
     }
 }
 
 /* bootsSymEncrypt of `count` bits, one warp per sample, written with stride kLweStride */
-__global__ void encrypt_kernel(uint64_t seed, int n, double stdev, int32_t mu, const int32_t *__restrict__ lwe_key,
+__global__ void encrypt_kernel(RngKeys keys, int n, double stdev, int32_t mu, const int32_t *__restrict__ lwe_key,
                                const int32_t *__restrict__ bits, int32_t *__restrict__ out, long long count)
 {
     const long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -175,14 +192,19 @@ __global__ void encrypt_kernel(uint64_t seed, int n, double stdev, int32_t mu, c
     if (s >= count) return;
     int32_t *o = out + (size_t)s * kLweStride;
     int32_t acc = 0;
-    for (int q = lane; q < kLweStride; q += 32) {
+    uint32_t blk[16];
+    for (int q = lane, k = 0; q < kLweStride; q += 32, k++) {
+        if ((k & 15) == 0) chacha20_block(keys.mask, ((uint64_t)s * 32 + lane) * 2 + (k >> 4), RNG_ENC_MASK, blk);
         int32_t v = 0;
-        if (q < n) { v = rnd_torus(seed, STREAM_ENC_A, (uint64_t)s * 1024 + q); acc += v * lwe_key[q]; }
+        if (q < n) { v = (int32_t)blk[k & 15]; acc += v * lwe_key[q]; }
         if (q != n) o[q] = v;
     }
 #pragma unroll
     for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (lane == 0) o[n] = acc + (bits[s] ? mu : -mu) + rnd_gauss_torus(seed, STREAM_ENC_E, (uint64_t)s, stdev);
+    if (lane == 0) {
+        chacha20_block(keys.secret, (uint64_t)s, RNG_ENC_NOISE, blk);
+        o[n] = acc + (bits[s] ? mu : -mu) + gauss_torus(blk[0], blk[1], stdev);
+    }
 }
 
 /* phase = b - <a, s>, one warp per sample */
@@ -200,7 +222,7 @@ __global__ void phase_kernel(int n, const int32_t *__restrict__ lwe_key, const i
     if (lane == 0) phases[s] = p[n] - acc;
 }
 
-cudaError_t launch_keygen(uint64_t seed, const DevParams &p, double ks_stdev, double bk_stdev, const int32_t *d_lwe_key,
+cudaError_t launch_keygen(const RngKeys &keys, const DevParams &p, double ks_stdev, double bk_stdev, const int32_t *d_lwe_key,
                           const int32_t *d_tlwe_key, double2 *d_shat, double2 *bkfft, int32_t *ksk, int32_t *bk_coef_export,
                           int32_t *ksk_export, cudaStream_t s)
 {
@@ -208,18 +230,18 @@ cudaError_t launch_keygen(uint64_t seed, const DevParams &p, double ks_stdev, do
     cudaError_t e = twiddle_ptrs(&tw2, &tw3);
     if (e != cudaSuccess) return e;
     keygen_sfft_kernel<<<1, 64, 0, s>>>(d_tlwe_key, d_shat, tw2, tw3);
-    keygen_bk_kernel<<<p.n * 2 * p.l, 64, 0, s>>>(seed, p.l, p.Bgbit, bk_stdev, d_lwe_key, d_shat, bkfft, bk_coef_export, tw2, tw3);
+    keygen_bk_kernel<<<p.n * 2 * p.l, 64, 0, s>>>(keys, p.l, p.Bgbit, bk_stdev, d_lwe_key, d_shat, bkfft, bk_coef_export, tw2, tw3);
     const int rows = kN * p.ks_t * ((1 << p.ks_basebit) - 1);
-    keygen_ksk_kernel<<<(rows * 32 + 255) / 256, 256, 0, s>>>(seed, p.n, p.ks_t, p.ks_basebit, ks_stdev, d_lwe_key, d_tlwe_key, ksk,
+    keygen_ksk_kernel<<<(rows * 32 + 255) / 256, 256, 0, s>>>(keys, p.n, p.ks_t, p.ks_basebit, ks_stdev, d_lwe_key, d_tlwe_key, ksk,
                                                              ksk_export, rows);
     return cudaGetLastError();
 }
-cudaError_t launch_encrypt(uint64_t seed, int n, double stdev, int32_t mu, const int32_t *d_lwe_key, const int32_t *d_bits,
+cudaError_t launch_encrypt(const RngKeys &keys, int n, double stdev, int32_t mu, const int32_t *d_lwe_key, const int32_t *d_bits,
                            int32_t *out, long long count, cudaStream_t s)
 {
     if (count <= 0) return cudaSuccess;
     const long long blocks = (count * 32 + 255) / 256;
-    encrypt_kernel<<<(unsigned)blocks, 256, 0, s>>>(seed, n, stdev, mu, d_lwe_key, d_bits, out, count);
+    encrypt_kernel<<<(unsigned)blocks, 256, 0, s>>>(keys, n, stdev, mu, d_lwe_key, d_bits, out, count);
     return cudaGetLastError();
 }
 cudaError_t launch_phase(int n, const int32_t *d_lwe_key, const int32_t *samples, int32_t *phases, long long count, cudaStream_t s)

@@ -1,10 +1,11 @@
 /* tfhe_io.cpp — see tfhe_io.h */
 #include "tfhe_io.h"
+#include "csprng.h"
 
 #include <cmath>
 #include <cstring>
 #include <map>
-#include <random>
+#include <new>
 
 namespace ieache {
 
@@ -85,7 +86,11 @@ int read_keyset_stream(FILE *f, HostKeySet &ks, bool want_bk, std::string &msg)
 {
     if (!read_param_blocks(f, ks.p, msg)) return IEACHE_ERR_FORMAT;
     const ieache_params &p = ks.p;
-    if (p.n <= 0 || p.N <= 0 || p.k <= 0 || p.bk_l <= 0 || p.ks_t <= 0 || p.ks_basebit <= 0 || p.n > 100000 || p.N > 65536) {
+    /* bounds before anything is shifted or allocated from these numbers (a hostile or damaged header must not turn
+     * into 1 << 40 or a terabyte resize): the widest values libtfhe's own parameter sets use are far inside them */
+    if (p.n <= 0 || p.N <= 0 || p.k <= 0 || p.bk_l <= 0 || p.ks_t <= 0 || p.ks_basebit <= 0 || p.bk_Bgbit <= 0 || p.n > 4096 ||
+        p.N > 4096 || p.k > 4 || p.bk_l > 16 || p.bk_Bgbit > 31 || p.bk_l * p.bk_Bgbit > 32 || p.ks_basebit > 8 || p.ks_t > 32 ||
+        p.ks_basebit * p.ks_t > 32) {
         msg = "implausible parameters in key file"; return IEACHE_ERR_FORMAT;
     }
     const int n = p.n, N = p.N, k = p.k, kpl = (k + 1) * p.bk_l, t = p.ks_t, base = 1 << p.ks_basebit;
@@ -93,8 +98,13 @@ int read_keyset_stream(FILE *f, HostKeySet &ks, bool want_bk, std::string &msg)
     int32_t id;
     double var;
     bool ok = rd(f, &id, 4) && rd(f, &id, 4);
-    if (want_bk) { ks.ksk.resize(nks * (n + 1)); ks.bk.resize((size_t)n * kpl * (k + 1) * N); }
-    std::vector<int32_t> scratch((size_t)(k + 1) * N > (size_t)n + 1 ? (size_t)(k + 1) * N : (size_t)n + 1);
+    std::vector<int32_t> scratch;
+    try {
+        if (want_bk) { ks.ksk.resize(nks * (n + 1)); ks.bk.resize((size_t)n * kpl * (k + 1) * N); }
+        scratch.resize((size_t)(k + 1) * N > (size_t)n + 1 ? (size_t)(k + 1) * N : (size_t)n + 1);
+    } catch (const std::bad_alloc &) {
+        msg = "out of memory for the key arrays"; return IEACHE_ERR_NOMEM;
+    }
     for (size_t s = 0; ok && s < nks; s++) {
         int32_t *dst = want_bk ? &ks.ksk[s * (n + 1)] : scratch.data();
         ok = rd(f, &id, 4) && rd(f, dst, 4 * (size_t)(n + 1)) && rd(f, &var, 8);
@@ -125,31 +135,34 @@ int write_keyset(const char *path, const HostKeySet &ks, bool with_secret, std::
     if (!f) { msg = std::string("cannot open ") + path; return IEACHE_ERR_IO; }
     const ieache_params &p = ks.p;
     const int n = p.n, N = p.N, k = p.k, kpl = (k + 1) * p.bk_l, t = p.ks_t, base = 1 << p.ks_basebit;
+    bool ok = true; /* every write is checked: a full disk must not leave a truncated 114 MB key reported as written */
+    auto put = [&](const void *src, size_t bytes) { ok = ok && fwrite(src, 1, bytes, f) == bytes; };
     write_param_blocks(f, p);
-    int32_t id = UID_BK; fwrite(&id, 4, 1, f);
-    id = UID_KS_KEY; fwrite(&id, 4, 1, f);
+    int32_t id = UID_BK; put(&id, 4);
+    id = UID_KS_KEY; put(&id, 4);
     const double var_ks = p.ks_stdev * p.ks_stdev, var_bk = p.bk_stdev * p.bk_stdev, zero = 0.0;
-    for (size_t s = 0; s < (size_t)k * N * t * base; s++) {
-        id = UID_LWE_SAMPLE; fwrite(&id, 4, 1, f);
-        fwrite(&ks.ksk[s * (n + 1)], 4, n + 1, f);
-        fwrite((s % base) ? &var_ks : &zero, 8, 1, f);
+    for (size_t s = 0; ok && s < (size_t)k * N * t * base; s++) {
+        id = UID_LWE_SAMPLE; put(&id, 4);
+        put(&ks.ksk[s * (n + 1)], 4 * (size_t)(n + 1));
+        put((s % base) ? &var_ks : &zero, 8);
     }
-    for (int i = 0; i < n; i++) {
-        id = UID_TGSW_SAMPLE; fwrite(&id, 4, 1, f);
+    for (int i = 0; ok && i < n; i++) {
+        id = UID_TGSW_SAMPLE; put(&id, 4);
         for (int r = 0; r < kpl; r++) {
-            id = UID_TLWE_SAMPLE; fwrite(&id, 4, 1, f);
-            fwrite(&ks.bk[((size_t)i * kpl + r) * (k + 1) * N], 4, (size_t)(k + 1) * N, f);
-            fwrite(&var_bk, 8, 1, f);
+            id = UID_TLWE_SAMPLE; put(&id, 4);
+            put(&ks.bk[((size_t)i * kpl + r) * (k + 1) * N], 4 * (size_t)(k + 1) * N);
+            put(&var_bk, 8);
         }
     }
     if (with_secret && ks.has_secret) {
-        id = UID_LWE_KEY; fwrite(&id, 4, 1, f);
-        fwrite(ks.lwe_key.data(), 4, n, f);
-        id = UID_TGSW_KEY; fwrite(&id, 4, 1, f);
-        fwrite(ks.tlwe_key.data(), 4, (size_t)k * N, f);
+        id = UID_LWE_KEY; put(&id, 4);
+        put(ks.lwe_key.data(), 4 * (size_t)n);
+        id = UID_TGSW_KEY; put(&id, 4);
+        put(ks.tlwe_key.data(), 4 * (size_t)k * N);
     }
-    fclose(f);
-    (void)msg;
+    ok = ok && !ferror(f);
+    if (fclose(f) != 0) ok = false;
+    if (!ok) { msg = std::string("short write on ") + path; return IEACHE_ERR_IO; }
     return IEACHE_OK;
 }
 
@@ -175,16 +188,23 @@ int write_samples(FILE *f, int n, const int32_t *src, size_t count, double varia
 
 void sym_encrypt_bits(const HostKeySet &ks, const int32_t *bits, size_t count, int32_t *out)
 {
-    static thread_local std::mt19937_64 gen{std::random_device{}()};
-    std::normal_distribution<double> gauss(0.0, ks.p.ks_stdev);
+    /* fresh 256-bit stream keys from the operating system for every call (csprng.h): masks from one key stream,
+     * noise from the other; Box-Muller as on the device */
+    RngKeys rk;
+    if (rng_keys_from_os(rk)) { fprintf(stderr, "ieache: getrandom failed\n"); abort(); }
     const int n = ks.p.n;
     const int32_t mu = 1 << 29;
+    uint32_t blk[16], nz[16];
+    uint64_t ctr = 0;
     for (size_t c = 0; c < count; c++) {
         int32_t *s = out + c * (n + 1);
-        const double e = gauss(gen);
+        chacha20_block(rk.secret, (uint64_t)c, RNG_ENC_NOISE, nz);
+        const double u1 = ((double)nz[0] + 1.0) * (1.0 / 4294967296.0), u2 = (double)nz[1] * (1.0 / 4294967296.0);
+        const double e = std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586476925286766559 * u2) * ks.p.ks_stdev;
         int32_t b = (bits[c] ? mu : -mu) + (int32_t)(int64_t)((e - std::floor(e + 0.5)) * 4294967296.0);
         for (int i = 0; i < n; i++) {
-            s[i] = (int32_t)(uint32_t)gen();
+            if ((i & 15) == 0) chacha20_block(rk.mask, ctr++, RNG_ENC_MASK, blk);
+            s[i] = (int32_t)blk[i & 15];
             b += s[i] * ks.lwe_key[i];
         }
         s[n] = b;

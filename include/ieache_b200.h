@@ -47,7 +47,7 @@ typedef struct ieache_params {
     double ks_stdev, bk_stdev, max_stdev;
 } ieache_params;
 
-typedef struct ieache_ctx ieache_ctx;           /* one per process and GPU */
+typedef struct ieache_ctx ieache_ctx;           /* one per GPU (several per process are fine: no process-wide state) */
 typedef struct ieache_cloudkey ieache_cloudkey; /* device-resident TFheGateBootstrappingCloudKeySet */
 typedef struct ieache_circuit ieache_circuit;   /* levelised gate DAG (Cloud/cloud.c circuits) */
 
@@ -66,24 +66,28 @@ int ieache_ctx_kernel_times(ieache_ctx *ctx, double *blind_rotate_ms, double *ke
                             uint64_t *blind_rotate_launches, uint64_t *keyswitch_launches, int reset);
 int ieache_ctx_set_timing(ieache_ctx *ctx, int enabled);
 
-/* Kernel selection: launches of at most `max_gates` gates use the two-group latency variant of the blind rotation
- * (one gate per CTA, one thread group per accumulator polynomial), larger ones the throughput variant unless its
- * last wave of 4 x SMs gates would be less than 90 % full.  0 forces the throughput variant for every size.
- * Process-wide; returns the previous value; a negative argument only queries.  Default 296 (one wave of two CTAs per SM). */
-int64_t ieache_set_wide_max(int64_t max_gates);
-/* Launches of at most max_gates gates (and at most the limit above) use the cluster latency kernel: one gate on a
- * pair of SMs (thread-block cluster of 2, products exchanged through distributed shared memory).  Same calling
- * convention as ieache_set_wide_max.  Default 74 (148 SMs / 2: one wave). */
-int64_t ieache_set_cluster_max(int64_t max_gates);
-/* Which compiled variant of the throughput blind rotation wide launches use: 41 (default) keeps the accumulators in
- * registers, one 64-thread group per gate; 60 is the warp-per-gate kernel (16 points per lane, accumulators in tensor
- * memory); 51/52/55/56 keep 64-thread groups with TMEM accumulators.  All give the same results (same parity tests);
- * a negative argument only queries.  Returns the previous value.  Tuning / test aid. */
-int ieache_set_throughput_variant(int variant);
-/* Key-switch launches of at least min_gates gates use the staged kernel (the key rows of one input position are
- * copied to shared memory once per 12 gates); smaller ones gather rows per gate.  Same calling convention.
- * Default 1000 (where the two kernels cross).  Both kernels give bit-identical results. */
-int64_t ieache_set_ks_staged_min(int64_t min_gates);
+/* Kernel selection (launch policy) of this context.  Every blind-rotation and key-switch kernel gives the same
+ * results (same parity tests); the policy only chooses the shape that is fastest for the size of a launch:
+ *   blind rotation   <= CLUSTER_MAX gates: one gate on a 2-CTA cluster (default 74: one wave of SM pairs);
+ *                    <= PAIR_MAX: one gate per CTA on two thread groups (default 296);
+ *                    >= W12_MIN: persistent kernel, one warp per gate, 12 gates per SM (default 900);
+ *                    between: one gate per 64-thread CTA, or the two-group kernel when that kernel's last wave of
+ *                    4 x SMs gates would be less than 90 % full
+ *   key switch       <= PAIR_MAX: 8-CTA cluster per gate; >= KS_STAGED_MIN (default 1000): row blocks staged by
+ *                    bulk copies and shared by 12 gates; between: per-gate gather
+ * THROUGHPUT_KERNEL pins the blind rotation of every launch above PAIR_MAX to IEACHE_KERNEL_GROUP or
+ * IEACHE_KERNEL_W12 (0 = by size, the default); any other value is IEACHE_ERR_ARG.  Thresholds must be >= 0.
+ * The setting belongs to the context: two contexts (two sessions, two GPUs) never see each other's.  old_value (may be
+ * NULL) receives the previous setting.  Tuning / test aid; the defaults are the measured crossovers. */
+enum { IEACHE_TUNE_CLUSTER_MAX = 1, IEACHE_TUNE_PAIR_MAX = 2, IEACHE_TUNE_W12_MIN = 3, IEACHE_TUNE_KS_STAGED_MIN = 4,
+       IEACHE_TUNE_THROUGHPUT_KERNEL = 5 };
+enum { IEACHE_KERNEL_CLUSTER = 1, IEACHE_KERNEL_PAIR = 2, IEACHE_KERNEL_GROUP = 41, IEACHE_KERNEL_W12 = 70 };
+enum { IEACHE_KS_CLUSTER = 1, IEACHE_KS_GATHER = 2, IEACHE_KS_STAGED = 3 };
+int ieache_ctx_set_tuning(ieache_ctx *ctx, int which, int64_t value, int64_t *old_value);
+/* which kernels a launch of `count` gates would use under the context's policy (IEACHE_KERNEL_*, IEACHE_KS_*) */
+int ieache_ctx_pick_kernels(const ieache_ctx *ctx, const ieache_cloudkey *key, int64_t count, int *blind_rotate, int *keyswitch);
+/* 352-sample operand / answer blocks the session calls have copied host->device and device->host on this context */
+int ieache_ctx_copy_counts(const ieache_ctx *ctx, uint64_t *h2d_value_blocks, uint64_t *d2h_value_blocks);
 /* step timer: CUDA events on the engine's stream (torch events only see torch's stream) */
 int ieache_ctx_timer_start(ieache_ctx *ctx);
 int ieache_ctx_timer_stop(ieache_ctx *ctx, double *elapsed_ms); /* records, synchronises, returns the elapsed device time */
@@ -114,17 +118,24 @@ int ieache_cloudkey_adopt_device(ieache_ctx *ctx, const ieache_params *p, void *
 
 /* ---- secret-key side on the GPU: Keygen/keygen.c, Client1/alice.c:117, Output/verif.c:93 ---- */
 typedef struct ieache_secretkey ieache_secretkey; /* LWE key (n bits) + TLWE key (N bits), host and device copies */
-/* new_random_gate_bootstrapping_secret_keyset (Keygen/keygen.c:30-36): draws both secret keys from
- * `seed` and builds the bootstrapping and key-switch keys directly in device layout.  If
- * bk_export / ksk_export are non-NULL they receive the libtfhe-order coefficient arrays
- * ([n][(k+1)l][k+1][N] and [kN][t][2^basebit][n+1]) so the key can be written to cloud.key. */
+/* new_random_gate_bootstrapping_secret_keyset (Keygen/keygen.c:30-36): draws both secret keys and builds the
+ * bootstrapping and key-switch keys directly in device layout.  If bk_export / ksk_export are non-NULL they receive
+ * the libtfhe-order coefficient arrays ([n][(k+1)l][k+1][N] and [kN][t][2^basebit][n+1]) so the key can be written to
+ * cloud.key.
+ * Randomness: ChaCha20 key streams under two independent 256-bit keys, one for the secret bits and the noise, one
+ * for the published masks.  seed == 0 (use this): both keys come from the operating system (getrandom).
+ * seed != 0: both keys are derived from the seed — reproducible key sets FOR TESTS ONLY; such a key set is exactly as
+ * secret as its 64-bit seed, and two key sets made from one seed are identical. */
 int ieache_keygen(ieache_ctx *ctx, const ieache_params *p, uint64_t seed, ieache_secretkey **sk, ieache_cloudkey **ck,
                   int32_t *bk_export, int32_t *ksk_export);
 int ieache_secretkey_import(ieache_ctx *ctx, const ieache_params *p, const int32_t *lwe_key, const int32_t *tlwe_key,
                             ieache_secretkey **sk);
 int ieache_secretkey_export(const ieache_secretkey *sk, int32_t *lwe_key /*n*/, int32_t *tlwe_key /*N, may be NULL*/);
 void ieache_secretkey_destroy(ieache_secretkey *sk);
-/* bootsSymEncrypt of `count` bits (host array) into device samples (stride IEACHE_DEVICE_STRIDE) */
+/* bootsSymEncrypt of `count` bits (host array) into device samples (stride IEACHE_DEVICE_STRIDE).
+ * seed == 0 (use this): fresh masks and noise from the operating system's entropy on every call.
+ * seed != 0: reproducible, FOR TESTS ONLY — two calls with the same seed use the same masks, which reveals the
+ * difference of their plaintexts. */
 int ieache_sym_encrypt_device(ieache_ctx *ctx, const ieache_secretkey *sk, const int32_t *bits, size_t count, int32_t *out_dev,
                               uint64_t seed);
 /* bootsSymDecrypt of device samples: bits (phase > 0) and, optionally, the raw phases, to host arrays */
@@ -187,7 +198,9 @@ int ieache_circuit_eval_device(ieache_ctx *ctx, const ieache_cloudkey *key, cons
 int ieache_cloud_run(ieache_ctx *ctx, const char *dir, double *seconds);
 
 /* ---- the callers on either side of the path, on the reference's files ---- */
-/* Keygen/keygen.c: writes secret.key, cloud.key, nbit.key into dir (p == NULL: lambda = 110 defaults) */
+/* Keygen/keygen.c: writes secret.key, cloud.key, nbit.key into dir (p == NULL: lambda = 110 defaults).
+ * seed_key / seed_nbit: 0 = operating-system entropy (use this); non-zero = reproducible, tests only (see ieache_keygen).
+ * Returns IEACHE_ERR_IO when a file cannot be written completely. */
 int ieache_keygen_files(ieache_ctx *ctx, const char *dir, const ieache_params *p, uint64_t seed_key, uint64_t seed_nbit);
 /* Client1/alice.c: one operand (sign code 0/2, width, 8 chunks least significant first) -> 352 records */
 int ieache_alice_encrypt(const char *dir, int32_t sign_code, int32_t width, const uint32_t *chunks, const char *out_path,

@@ -112,7 +112,8 @@ void o_mul128(const OKeySet *ck, Torus32 *r[5], const Torus32 *a, const Torus32 
     for (int q = 0; q < 5; q++) sums[q] = arr32(ck);
     const Torus32 *x[4] = {a, b, c, d};
     mulK(ck, 4, sums, x, e, carry);
-    for (int q = 0; q < 5; q++) { copy32(ck, r[q], sums[4 - q]); free(sums[q]); }
+    for (int q = 0; q < 5; q++) copy32(ck, r[q], sums[4 - q]);
+    for (int q = 0; q < 5; q++) free(sums[q]);
 }
 
 /* Client1/alice.c:58-66,116-149,167-189 */
@@ -174,7 +175,8 @@ int o_cloud_main(const OKeySet *ck, const OKeySet *nbitkey, int32_t int_op, cons
     int32_t n1 = dec32(nbitkey, neg1), n2 = dec32(nbitkey, neg2);                      /* :780-796 */
     if (n1 == 2) n1 = 1;                                                               /* :788-789 */
     const int32_t int_negative = n1 + n2;                                              /* :804 */
-    const int32_t code = int_negative == 3 ? 4 : int_negative;                         /* :812-821 */
+    /* :812-821: 1 -> 1, 2 -> 2, 3 -> 4 and 0 for every other sum (e.g. a chained operand that already carries code 4) */
+    const int32_t code = int_negative == 1 ? 1 : int_negative == 2 ? 2 : int_negative == 3 ? 4 : 0;
     enc32(nbitkey, code, answer, seed * 4 + 1);                                        /* :822-826 */
     int32_t int_bit;
     if (int_op == 4) {                                                                 /* :833-843 */

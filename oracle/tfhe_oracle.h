@@ -84,6 +84,8 @@ void o_gate_batch(const OKeySet *ks, int op, Torus32 *out, const Torus32 *a, con
 void o_bootstrap_woks(const OKeySet *ks, Torus32 *out_extracted /*kN+1*/, Torus32 mu,
                       const Torus32 *x /*n+1*/);
 void o_keyswitch(const OKeySet *ks, Torus32 *out /*n+1*/, const Torus32 *u /*kN+1*/);
+/* exact_ref.c: o_bootstrap_woks with the external products in exact integer arithmetic (no transform, no rounding) */
+void o_bootstrap_woks_exact(const OKeySet *ks, Torus32 *out_extracted /*kN+1*/, Torus32 mu, const Torus32 *x /*n+1*/);
 int o_max_threads(void);
 
 /* libtfhe-format files (SURVEY App. A "Serialisation", recalled). */

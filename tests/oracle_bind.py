@@ -49,6 +49,7 @@ def _lib():
         L.o_phase_extracted.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p]
         L.o_gate_batch.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int]
         L.o_bootstrap_woks.argtypes = [c_void_p, c_void_p, c_int32, c_void_p]
+        L.o_bootstrap_woks_exact.argtypes = [c_void_p, c_void_p, c_int32, c_void_p]
         L.o_keyswitch.argtypes = [c_void_p, c_void_p, c_void_p]
         L.o_write_cloud_key.argtypes = [c_void_p, c_char_p]
         L.o_write_secret_key.argtypes = [c_void_p, c_char_p]
@@ -137,6 +138,13 @@ class KeySet:
         out = np.zeros((len(x), self.p.k * self.p.N + 1), dtype=np.int32)
         for i in range(len(x)):
             _lib().o_bootstrap_woks(self._h, _vp(out[i]), mu, _vp(np.ascontiguousarray(x[i])))
+        return out
+
+    def bootstrap_woks_exact(self, x: np.ndarray, mu: int = 1 << 29) -> np.ndarray:
+        """oracle/exact_ref.c: the same blind rotation in exact integer arithmetic (schoolbook products, no transform)"""
+        out = np.zeros((len(x), self.p.k * self.p.N + 1), dtype=np.int32)
+        for i in range(len(x)):
+            _lib().o_bootstrap_woks_exact(self._h, _vp(out[i]), mu, _vp(np.ascontiguousarray(x[i])))
         return out
 
     def keyswitch(self, ext: np.ndarray) -> np.ndarray:

@@ -73,3 +73,43 @@ def test_batched_ingest_of_request_directories(tmp_path, pkg):
         value, code, width = pkg.verif_run(d)
         assert value == w and width == (64 if op == 4 else 32), (d, value, code, width, w)
     sess.close(); eng.close()
+
+
+# ------------------------------------------------------------------ the reference's own cloud.c on this library
+REF_B200 = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "cloud_ref_b200")
+REF_CASES = [(1, 0, 0, 32, 1 << 30, 1 << 30), (1, 2, 2, 32, 5, 7), (2, 0, 0, 32, 1, 1000), (1, 2, 0, 32, 50, 20),
+             (2, 0, 0, 64, (1 << 63) + 5, (1 << 62) + 77), (4, 2, 0, 32, 77777, 99999)]
+
+
+@pytest.mark.skipif(not os.path.exists(REF_B200), reason="oracle/_ref/cloud_ref_b200 not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("op,s1,s2,width,a,b", REF_CASES)
+def test_unmodified_reference_cloud_c_on_the_gpu_library(tmp_path, pkg, oracle, op, s1, s2, width, a, b):
+    """SURVEY 8 b1 executed: /root/reference/Cloud/cloud.c compiled UNMODIFIED against include/tfhe/*.h and linked with
+    libieache_b200.so instead of libtfhe (oracle/Makefile), run as ./cloud is run (Cloud/dragonfly_cipher_cloud.py:1233)
+    on oracle-written cloud.key / nbit.key / cloud.data / operator.txt.  Its answer.data must decrypt to what
+    ieache_cloud_run writes for the same files (the levelised GPU circuits) and to what the oracle's cloud main() gives."""
+    import subprocess
+    from test_reference_cloud import write_request
+    ks = oracle.keygen(ob.params_default(8), seed=31)
+    nbit = oracle.keygen(ob.params_default(8), seed=32)
+    d = str(tmp_path)
+    data = write_request(d, oracle, ks, nbit, op, s1, s2, width, a, b)
+    r = subprocess.run([REF_B200], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "Computation Time:" in r.stdout
+    ans_ref = ks.read_samples(os.path.join(d, "answer.data"), 352)
+    assert len(ans_ref) == 352
+    eng = pkg.Engine(0)
+    rc, _ = eng.cloud_run(d)
+    assert rc == 0
+    ans_gpu = ks.read_samples(os.path.join(d, "answer.data"), 352)
+    rc_o, ans_o = oracle.cloud_main(ks, nbit, op, data)
+    v = oracle.verif(ks, nbit, ans_ref)
+    assert v == oracle.verif(ks, nbit, ans_gpu) == oracle.verif(ks, nbit, ans_o)
+    va, vb = (-a if s1 == 2 else a), (-b if s2 == 2 else b)
+    assert ob.decode_result(op, *v) == {1: va + vb, 2: va - vb, 4: va * vb}[op]
+    # padding and carry blocks are verbatim copies of operand 1's carry block in all three (cloud.c:901-916)
+    nres = (2 * width if op == 4 else width) // 32
+    for ans in (ans_ref, ans_gpu, ans_o):
+        assert (ans[(2 + nres) * 32:(3 + nres) * 32] == data[320:352]).all() and (ans[320:352] == data[320:352]).all()
+    eng.close(); ks.free(); nbit.free()
