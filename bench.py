@@ -9,6 +9,11 @@ host<->device copies inside the timed region.  N > 1 (torchrun): every rank owns
 is generated on rank 0 and broadcast once over NCCL, each rank runs its own 2^20 gates (weak scaling,
 no data-path collective), time = max over ranks.
 
+Every line also carries `expression_batch`: BASELINE.json configs 4 and 5 time-boxed per GPU (512 independent a*b+c
+expressions and 128 independent 64-bit multiplies per GPU through the levelised circuits, sharded by expression,
+every result decrypted and checked on its rank), so that the scaling record holds the circuit workloads next to the
+independent gates.
+
 `--impl reference` times the CPU restatement of libtfhe (oracle/, kind "port": libtfhe itself is not in
 /root/reference nor in the image) on all host threads, on a bounded sample of the same workload.
 """
@@ -34,6 +39,18 @@ N_LWE = 630
 FLOP_PER_BOOTSTRAP = 163e6   # n*[(kpl+k+1)*F_T(1024) + kpl*(k+1)*(N/2)*8], FP64
 BK_BYTES = 61_931_520        # transform-domain bootstrapping key
 KS_BYTES_GATHERED = 15_507_456  # expected key-switch rows gathered per gate
+
+
+PARAMS_STR = "n=630,N=1024,k=1,l=3,Bgbit=7,t=8,basebit=2"
+LIBTFHE_ADVERTISED_MS_PER_GATE = 13.0   # tfhe.github.io: "about 13 ms per binary gate" (spqlios-fma, one core, other hardware)
+KERNEL_NAMES = {1: "blind_rotate_cluster_kernel<3>", 2: "blind_rotate_pair_kernel<3>", 41: "blind_rotate_kernel<3,0,true>",
+                70: "blind_rotate_w12_kernel<3>"}
+
+
+def workload_config(log2_gates: int, world: int) -> dict:
+    """identical in the b200 arm and in the reference arm: the workload, not the run"""
+    return {"workload": f"bootsNAND_batch_2^{log2_gates}_per_gpu", "gates_per_step_per_gpu": 1 << log2_gates, "params": PARAMS_STR,
+            "parallelism": f"dp{world} (key replicated, no data-path collective)"}
 
 
 class ClockSampler:
@@ -138,13 +155,18 @@ def run_reference(args):
     total = sum(d for _, d, _ in rates)
     secs = sum(t for _, _, t in rates)
     value = total / secs
-    sample = f"{rates[0][1]} independent bootsNAND per step on {threads} host threads (bounded sample of the 2^20-gate workload)"
+    sample = f"{rates[0][1]} independent bootsNAND per step on {threads} host threads (bounded sample of the 2^{args.log2_gates}-gate workload)"
+    single_ms = cpu_port_single_thread_ms(20)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, len(rates)), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32 torus + f64 transform", "data": "synthetic",
-        "config": {"workload": "bootsNAND_batch_2^20_per_gpu", "params": "n=630,N=1024,k=1,l=3,Bgbit=7,t=8,basebit=2"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": workload_config(args.log2_gates, max(1, world)),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "single_thread_ms_per_gate": single_ms,
+                         "port_vs_advertised_libtfhe": single_ms / LIBTFHE_ADVERTISED_MS_PER_GATE,
+                         "note": "the port is slower per gate than libtfhe advertises for spqlios-fma (13 ms): ratios against this arm are "
+                                 "ratios against our port, not against libtfhe"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -152,18 +174,25 @@ def run_reference(args):
     return 0
 
 
-def run_circuit_workload(args, m, eng, sk, key, rank, world, local, t_bcast_ms):
-    """BASELINE.json configs 4 / 5, time-boxed: --n-expr independent expressions per GPU and step through the levelised
-    circuit (every level = one blind-rotation + one key-switch launch over all expressions); sharded by expression,
-    cloud key replicated, no data-path collective.  A step = one evaluation of all expressions of this rank."""
+CIRCUIT_WORKLOADS = {
+    "muladd": ("a*b+c on 32-bit operands (mul32 then 64-bit add, Cloud/cloud.c:115-218 + :18-51)", "4"),
+    "mul64": ("64-bit multiply (2 x mul64 + split, Cloud/cloud.c:2568-2616)", "5"),
+}
+
+
+def expression_batch(m, eng, sk, key, rank, world, which: str, n_expr: int, steps: int = 1, warmup: int = 0):
+    """`n_expr` independent expressions PER GPU through the levelised circuit (every level = one blind-rotation + one
+    key-switch launch over all expressions of the rank); expression e of the whole job is drawn from seed (base, e) and
+    lives on rank e // n_expr (contiguous shards, ie-ache_b200/dist.py shard_range); no data-path collective.  Every
+    decrypted result is checked against the plaintext arithmetic on its rank.  Returns the aggregate figures."""
     import torch
     import torch.distributed as dist
-    kind, width, name = (m.CIRC_MULADD, 32, "a*b+c (mul32 then 64-bit add)") if args.workload == "muladd" else (m.CIRC_MUL, 64, "64-bit multiply (2 x mul64 + split)")
+    from ieache_b200.dist import shard_range
+    kind, width = (m.CIRC_MULADD, 32) if which == "muladd" else (m.CIRC_MUL, 64)
     circ = eng.circuit(kind, width)
-    n_expr = args.n_expr
-    rng = np.random.default_rng(4000 + rank)
+    lo, hi = shard_range(world * n_expr, rank, world)
     nw = circ.n_inputs // 32
-    vals = rng.integers(0, 2 ** 31, size=(n_expr, nw), dtype=np.int64)
+    vals = np.stack([np.random.default_rng([4000, e]).integers(0, 2 ** 31, size=nw, dtype=np.int64) for e in range(lo, hi)])
     vals[:, -1] = 0                                   # carry block: encryptions of 0
     if kind == m.CIRC_MULADD:
         vals[:, 3] = 0                                # high chunk of c
@@ -178,17 +207,14 @@ def run_circuit_workload(args, m, eng, sk, key, rank, world, local, t_bcast_ms):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         eng.eval_device(key, circ, d_in, d_res, n_expr)
-    sampler = ClockSampler(local)
     barrier()
     launches0 = eng.launch_count
-    sampler.start()
     eng.timer_start()
-    for _ in range(args.steps):
+    for _ in range(steps):
         eng.eval_device(key, circ, d_in, d_res, n_expr)
     ms_total = eng.timer_stop()
-    clocks = sampler.stop()
     barrier()
     launches = eng.launch_count - launches0
     if world > 1:
@@ -202,19 +228,31 @@ def run_circuit_workload(args, m, eng, sk, key, rank, world, local, t_bcast_ms):
         v = [int(x) for x in vals[e]]
         want = v[0] * v[1] + v[2] if kind == m.CIRC_MULADD else (v[0] | v[1] << 32) * (v[2] | v[3] << 32)
         if got != want:
-            raise SystemExit(f"rank {rank}: expression {e} decrypts to {got}, expected {want}")
-    value = world * n_expr * circ.bootstraps * args.steps / (ms_total * 1e-3)
+            raise SystemExit(f"rank {rank}: expression {lo + e} decrypts to {got}, expected {want}")
+    eng.device_free(d_in); eng.device_free(d_res)
+    name, cfg = CIRCUIT_WORKLOADS[which]
+    return {"workload": f"{n_expr} independent {name} per GPU: {circ.bootstraps} bootstraps, {circ.levels} levels each "
+                        f"(time-boxed subset of BASELINE.json config {cfg})",
+            "n_expr_per_gpu": n_expr, "n_gpus": world, "gates_per_s": world * n_expr * circ.bootstraps * steps / (ms_total * 1e-3),
+            "ms_per_step": ms_total / steps, "ms_per_expression": ms_total / steps / n_expr, "gpu_launches": launches,
+            "verified": "every decrypted result equals the plaintext arithmetic on its rank"}
+
+
+def run_circuit_workload(args, m, eng, sk, key, rank, world, local, bcast):
+    """--workload muladd / mul64: the circuit workload as the whole bench line"""
+    import torch.distributed as dist
+    sampler = ClockSampler(local)
+    sampler.start()
+    r = expression_batch(m, eng, sk, key, rank, world, args.workload, args.n_expr, steps=args.steps, warmup=args.warmup)
+    clocks = sampler.stop()
     if rank == 0:
         print(json.dumps({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": r["gates_per_s"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32 torus + f64 transform", "data": "synthetic",
-            "config": {"workload": f"{n_expr} independent {name} per GPU and step: {circ.bootstraps} bootstraps, {circ.levels} levels each "
-                                   f"(time-boxed subset of BASELINE.json config {'4' if kind == m.CIRC_MULADD else '5'})",
-                       "params": "n=630,N=1024,k=1,l=3,Bgbit=7,t=8,basebit=2", "parallelism": f"dp{world} by expression (key replicated, no data-path collective)",
-                       "ms_per_expression": ms_total / args.steps / n_expr, "key_broadcast_ms": t_bcast_ms,
-                       "verified": "every decrypted result equals the plaintext arithmetic"},
-            "e2e": None, "gpu_launches": launches, "clocks": clocks, "roofline": None, "cpu_baseline": None}), flush=True)
+            "config": {"workload": r["workload"], "params": PARAMS_STR, "parallelism": f"dp{world} by expression (key replicated, no data-path collective)"},
+            "run_info": {"ms_per_expression": r["ms_per_expression"], "key_replication": bcast, "verified": r["verified"]},
+            "e2e": None, "gpu_launches": r["gpu_launches"], "clocks": clocks, "roofline": None, "cpu_baseline": None}), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -234,6 +272,8 @@ def main():
                          "configs 4 / 5 (independent a*b+c expressions / 64-bit multiplies, --n-expr per GPU) through the levelised circuits")
     ap.add_argument("--n-expr", type=int, default=64, help="expressions per GPU and step for --workload muladd / mul64")
     ap.add_argument("--ref-seconds", type=float, default=0.0, help="--impl reference: seconds of CPU work per step (default: sized so the run ends within ~2 minutes)")
+    ap.add_argument("--batch-muladd", type=int, default=512, help="expression_batch: a*b+c expressions per GPU (0 = skip)")
+    ap.add_argument("--batch-mul64", type=int, default=128, help="expression_batch: 64-bit multiplies per GPU (0 = skip)")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-expression", action="store_true")
     args = ap.parse_args()
@@ -252,8 +292,14 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: there is no CPU fallback for the engine (use --impl reference for the CPU port)")
     torch.cuda.set_device(local)
+    nccl_init_ms = 0.0
     if world > 1:
+        t0 = time.perf_counter()
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        warm = torch.zeros(1, device="cuda")
+        dist.all_reduce(warm)                      # communicator bring-up (rings / NVLS setup) happens on the first collective
+        torch.cuda.synchronize()
+        nccl_init_ms = 1e3 * (time.perf_counter() - t0)
     eng = m.Engine(local)
     params = m.Params.default(N_LWE)
     count = 1 << args.log2_gates
@@ -267,23 +313,25 @@ def main():
         sk = key = None
         lwe = np.zeros(N_LWE, dtype=np.int32)
         tlwe = np.zeros(1024, dtype=np.int32)
-    t_bcast_ms = 0.0
+    bcast = {"nccl_init_ms": nccl_init_ms, "broadcast_ms": 0.0, "bytes": 0}
     if world > 1:
         from ieache_b200 import dist as idist
-        torch.cuda.synchronize()
-        tb = time.perf_counter()
-        key, keep = idist.broadcast_cloud_key(eng, key, params, src=0)
+        timings = {}
+        key, keep = idist.broadcast_cloud_key(eng, key, params, src=0, timings=timings)
+        bcast.update(broadcast_ms=timings["broadcast_ms"], bytes=timings["bytes"],
+                     GBps=timings["bytes"] / (timings["broadcast_ms"] * 1e-3) / 1e9 if timings["broadcast_ms"] else None,
+                     note="nccl_init_ms = init_process_group + first collective (communicator bring-up); broadcast_ms = the two "
+                          "key arrays, CUDA events around the NCCL broadcasts, max over ranks")
         kt = torch.from_numpy(np.concatenate([lwe, tlwe])).cuda()
-        dist.broadcast(kt, src=0)
+        dist.broadcast(kt, src=0)                   # the bench's own decryption key (a test fixture, not part of the path)
         torch.cuda.synchronize()
-        t_bcast_ms = 1e3 * (time.perf_counter() - tb)
         if rank != 0:
             both = kt.cpu().numpy()
             lwe, tlwe = both[:N_LWE].copy(), both[N_LWE:].copy()
             sk = eng.secret_key_import(params, lwe, tlwe)
 
     if args.workload != "nand":
-        return run_circuit_workload(args, m, eng, sk, key, rank, world, local, t_bcast_ms)
+        return run_circuit_workload(args, m, eng, sk, key, rank, world, local, bcast)
 
     # ---- synthetic ciphertexts, made on the GPU (Client/alice.c's role): 2 x count samples, resident in HBM
     rng = np.random.default_rng(1000 + rank)
@@ -343,24 +391,28 @@ def main():
     br_ms = kt["blind_rotate_ms"] / br_launches
     gates_per_launch = count * args.steps / br_launches
     achieved_tflops = FLOP_PER_BOOTSTRAP * gates_per_launch / (br_ms * 1e-3) / 1e12
-    traffic = None
+    br_kernel = eng.pick_kernels(key, int(gates_per_launch))[0]
+    traffic, traffic_source = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("blind_rotate_dram_bytes_per_launch")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if tj.get("kernel") == KERNEL_NAMES.get(br_kernel):
+            traffic = tj.get("blind_rotate_dram_bytes_per_launch")
+            traffic_source = "static: ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch of this size, " + tj.get("source", "profiles/")
     except (OSError, ValueError):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     # memory view: BK streamed once per launch (reuse across all gates of the launch) + per-gate inputs/outputs
     alg_bytes = BK_BYTES + gates_per_launch * (2 * 2524 + 4100)
     roofline = {
-        "kernel": "blind_rotate_kernel<L=3,G=1,MINB=4,ROLL=0,ACCREG>", "bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
-        "frac": achieved_tflops / fp64_peak if fp64_peak else None, "traffic": traffic,
+        "kernel": KERNEL_NAMES.get(br_kernel, str(br_kernel)), "bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+        "frac": achieved_tflops / fp64_peak if fp64_peak else None, "traffic": traffic, "traffic_source": traffic_source,
         "peak_source": "dense FP64 FMA microbenchmark run live by this bench (MEASURED_PEAKS.json has no FP64 figure)",
         "flop_per_gate": FLOP_PER_BOOTSTRAP, "gates_per_launch": gates_per_launch, "ms_per_launch": br_ms,
         "share_of_step": kt["blind_rotate_ms"] / ms_total if world == 1 else None,
         "hbm_view": {"bound": "hbm", "achieved": alg_bytes / (br_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                      "frac": alg_bytes / (br_ms * 1e-3) / 1e9 / hbm_peak,
                      "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                     "note": "algorithmic bytes = BK once per launch + 2 inputs + 1 extracted sample per gate; the kernel is FP64/LSU-bound, not HBM-bound"},
+                     "note": "algorithmic bytes = BK once per launch + 2 inputs + 1 extracted sample per gate; the kernel is bound by FP64 issue, not by HBM"},
         "keyswitch": {"ms_per_launch": kt["keyswitch_ms"] / max(1, kt["keyswitch_launches"]),
                       "achieved_GBps": KS_BYTES_GATHERED * gates_per_launch / (kt["keyswitch_ms"] / max(1, kt["keyswitch_launches"]) * 1e-3) / 1e9,
                       "share_of_step": kt["keyswitch_ms"] / ms_total if world == 1 else None},
@@ -437,6 +489,15 @@ def main():
                       "reference_paper": "A+B*C 329 s on a single-core i7 VM (AC058.pdf p.4, whole run, other hardware)",
                       "verified": "decrypted results equal a*b+c"}
 
+    # ---- BASELINE.json configs 4 / 5, time-boxed per GPU, at every N ------------------------------------
+    batches = {}
+    if args.batch_muladd > 0:
+        batches["muladd"] = expression_batch(m, eng, sk, key, rank, world, "muladd", args.batch_muladd)
+    if args.batch_mul64 > 0:
+        batches["mul64"] = expression_batch(m, eng, sk, key, rank, world, "mul64", args.batch_mul64)
+    for b in batches.values():
+        b["fraction_of_nand_rate"] = b["gates_per_s"] / value
+
     # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1:
@@ -444,17 +505,19 @@ def main():
         cpu = {"value": r, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{done} independent bootsNAND in {dt:.1f} s on {threads} threads (oracle/: C restatement of libtfhe, default parameters)",
                "single_thread_ms_per_gate": cpu_port_single_thread_ms(100 if args.cpu_seconds >= 5 else 10)}
+        cpu["port_vs_advertised_libtfhe"] = cpu["single_thread_ms_per_gate"] / LIBTFHE_ADVERTISED_MS_PER_GATE
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32 torus + f64 transform", "data": "synthetic",
-            "config": {"workload": f"bootsNAND_batch_2^{args.log2_gates}_per_gpu", "gates_per_step_per_gpu": count,
-                       "params": "n=630,N=1024,k=1,l=3,Bgbit=7,t=8,basebit=2", "parallelism": f"dp{world} (key replicated, no data-path collective)",
-                       "l2": f"inputs {2 * count * 2528 / 1e9:.1f} GB per GPU, larger than L2 (126 MB); no flush needed",
-                       "key_broadcast_ms": t_bcast_ms, "verified": f"{len(sub)} decrypted results per rank against the NAND truth table"},
+            "config": workload_config(args.log2_gates, world),
+            "run_info": {"l2": f"inputs {2 * count * 2528 / 1e9:.1f} GB per GPU, larger than L2 (126 MB); no flush needed",
+                         "key_replication": bcast, "verified": f"{len(sub)} decrypted results per rank against the NAND truth table",
+                         "blind_rotate_kernel": KERNEL_NAMES.get(br_kernel, str(br_kernel))},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "expression": expression,
+            "expression_batch": batches,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -45,6 +45,17 @@ static int fail(int code, const char *fmt, ...)
         if (e__ != cudaSuccess) return fail(IEACHE_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); \
     } while (0)
 
+/* device allocation that is released on every exit path (the CU() macro returns early on errors) */
+struct DevBuf {
+    void *p = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes); }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
 extern "C" const char *ieache_last_error(void) { return g_err.c_str(); }
 extern "C" const char *ieache_version(void) { return "ieache_b200 0.1 (sm_100a)"; }
 
@@ -301,6 +312,8 @@ extern "C" int ieache_cloudkey_device_sizes(const ieache_params *p, size_t *bkff
     return IEACHE_OK;
 }
 
+extern "C" void ieache_cloudkey_destroy(ieache_cloudkey *key);
+
 extern "C" int ieache_cloudkey_create(ieache_ctx *ctx, const ieache_params *p, const int32_t *bk, const int32_t *ksk,
                                       ieache_cloudkey **out)
 {
@@ -308,25 +321,25 @@ extern "C" int ieache_cloudkey_create(ieache_ctx *ctx, const ieache_params *p, c
     int rc = check_params(p);
     if (rc) return rc;
     CU(cudaSetDevice(ctx->device));
-    std::unique_ptr<ieache_cloudkey> key(new ieache_cloudkey());
+    /* the key object owns its arrays from the moment they exist: an early return frees them through the deleter */
+    std::unique_ptr<ieache_cloudkey, void (*)(ieache_cloudkey *)> key(new ieache_cloudkey(), ieache_cloudkey_destroy);
     key->ctx = ctx; key->p = *p; fill_dev_params(*p, key->dp);
     ieache_cloudkey_device_sizes(p, &key->bkfft_bytes, &key->ksk_bytes);
     const int kpl = 2 * p->bk_l, base = 1 << p->ks_basebit;
     const size_t bk_words = (size_t)p->n * kpl * 2 * 1024;
     const size_t ksk_words = (size_t)1024 * p->ks_t * base * (p->n + 1);
-    int32_t *d_tmp = nullptr;
+    DevBuf tmp;
     CU(cudaMalloc((void **)&key->bkfft, key->bkfft_bytes));
     CU(cudaMalloc((void **)&key->ksk, key->ksk_bytes));
-    CU(cudaMalloc((void **)&d_tmp, std::max(bk_words, ksk_words) * sizeof(int32_t)));
+    CU(tmp.alloc(std::max(bk_words, ksk_words) * sizeof(int32_t)));
     /* bkFFT on the GPU (libtfhe builds it on the CPU at key load) */
-    CU(cudaMemcpyAsync(d_tmp, bk, bk_words * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    CU(launch_bk_fft(d_tmp, key->bkfft, p->n * kpl * 2, ctx->stream));
+    CU(cudaMemcpyAsync(tmp.p, bk, bk_words * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(launch_bk_fft(tmp.as<int32_t>(), key->bkfft, p->n * kpl * 2, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    CU(cudaMemcpyAsync(d_tmp, ksk, ksk_words * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    CU(launch_pack_ksk(d_tmp, key->ksk, 1024, p->ks_t, base, p->n, ctx->stream));
+    CU(cudaMemcpyAsync(tmp.p, ksk, ksk_words * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(launch_pack_ksk(tmp.as<int32_t>(), key->ksk, 1024, p->ks_t, base, p->n, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->launches += 2;
-    cudaFree(d_tmp);
     *out = key.release();
     return IEACHE_OK;
 }
@@ -445,17 +458,16 @@ extern "C" int ieache_keygen(ieache_ctx *ctx, const ieache_params *p, uint64_t s
     CU(cudaMalloc((void **)&key->ksk, key->ksk_bytes));
     const int kpl = 2 * p->bk_l, base = 1 << p->ks_basebit;
     const size_t bk_words = (size_t)p->n * kpl * 2 * 1024, ksk_words = (size_t)1024 * p->ks_t * base * (p->n + 1);
-    double2 *d_shat = nullptr;
-    int32_t *d_bk = nullptr, *d_ks = nullptr;
-    CU(cudaMalloc((void **)&d_shat, 512 * sizeof(double2)));
-    if (bk_export) CU(cudaMalloc((void **)&d_bk, bk_words * 4));
-    if (ksk_export) { CU(cudaMalloc((void **)&d_ks, ksk_words * 4)); CU(cudaMemsetAsync(d_ks, 0, ksk_words * 4, ctx->stream)); }
-    CU(launch_keygen(rk, key->dp, p->ks_stdev, p->bk_stdev, sk->d_lwe_key, sk->d_tlwe_key, d_shat, key->bkfft, key->ksk, d_bk, d_ks, ctx->stream));
+    DevBuf shat, dbk, dks;
+    CU(shat.alloc(512 * sizeof(double2)));
+    if (bk_export) CU(dbk.alloc(bk_words * 4));
+    if (ksk_export) { CU(dks.alloc(ksk_words * 4)); CU(cudaMemsetAsync(dks.p, 0, ksk_words * 4, ctx->stream)); }
+    CU(launch_keygen(rk, key->dp, p->ks_stdev, p->bk_stdev, sk->d_lwe_key, sk->d_tlwe_key, shat.as<double2>(), key->bkfft, key->ksk,
+                     dbk.as<int32_t>(), dks.as<int32_t>(), ctx->stream));
     ctx->launches += 3;
-    if (bk_export) CU(cudaMemcpyAsync(bk_export, d_bk, bk_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (ksk_export) CU(cudaMemcpyAsync(ksk_export, d_ks, ksk_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (bk_export) CU(cudaMemcpyAsync(bk_export, dbk.p, bk_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ksk_export) CU(cudaMemcpyAsync(ksk_export, dks.p, ksk_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_shat); cudaFree(d_bk); cudaFree(d_ks);
     *sk_out = skg.release();
     *ck_out = key.release();
     return IEACHE_OK;
@@ -466,8 +478,9 @@ extern "C" int ieache_sym_encrypt_device(ieache_ctx *ctx, const ieache_secretkey
     if (!ctx || !sk || !bits || !out_dev) return fail(IEACHE_ERR_ARG, "null argument");
     if (count == 0) return IEACHE_OK;
     CU(cudaSetDevice(ctx->device));
-    int32_t *d_bits = nullptr;
-    CU(cudaMalloc((void **)&d_bits, count * 4));
+    DevBuf dbits;
+    CU(dbits.alloc(count * 4));
+    int32_t *d_bits = dbits.as<int32_t>();
     CU(cudaMemcpyAsync(d_bits, bits, count * 4, cudaMemcpyHostToDevice, ctx->stream));
     RngKeys rk;
     if (seed == 0) { if (rng_keys_from_os(rk)) return fail(IEACHE_ERR_IO, "getrandom failed"); } /* fresh masks and noise per call */
@@ -475,7 +488,6 @@ extern "C" int ieache_sym_encrypt_device(ieache_ctx *ctx, const ieache_secretkey
     CU(launch_encrypt(rk, sk->p.n, sk->p.ks_stdev, 1 << 29, sk->d_lwe_key, d_bits, out_dev, (long long)count, ctx->stream));
     ctx->launches++;
     CU(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_bits);
     return IEACHE_OK;
 }
 extern "C" int ieache_sym_decrypt_device(ieache_ctx *ctx, const ieache_secretkey *sk, const int32_t *samples_dev, size_t count,
@@ -484,14 +496,14 @@ extern "C" int ieache_sym_decrypt_device(ieache_ctx *ctx, const ieache_secretkey
     if (!ctx || !sk || !samples_dev || (!bits && !phases)) return fail(IEACHE_ERR_ARG, "null argument");
     if (count == 0) return IEACHE_OK;
     CU(cudaSetDevice(ctx->device));
-    int32_t *d_ph = nullptr;
-    CU(cudaMalloc((void **)&d_ph, count * 4));
+    DevBuf dph;
+    CU(dph.alloc(count * 4));
+    int32_t *d_ph = dph.as<int32_t>();
     CU(launch_phase(sk->p.n, sk->d_lwe_key, samples_dev, d_ph, (long long)count, ctx->stream));
     ctx->launches++;
     std::vector<int32_t> ph(count);
     CU(cudaMemcpyAsync(ph.data(), d_ph, count * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_ph);
     if (phases) memcpy(phases, ph.data(), count * 4);
     if (bits) for (size_t i = 0; i < count; i++) bits[i] = ph[i] > 0 ? 1 : 0;
     return IEACHE_OK;
@@ -739,7 +751,7 @@ struct ieache_circuit {
     int device = -1;
     GateT *d_tmpl = nullptr;
     std::vector<size_t> level_off;
-    GateT *d_out_refs = nullptr; /* unused for now */
+    int32_t *d_out_slots = nullptr; /* wire slot of every output, uploaded with the templates */
 };
 
 extern "C" int ieache_circuit_build(int kind, int width, ieache_circuit **out)
@@ -753,7 +765,7 @@ extern "C" int ieache_circuit_build(int kind, int width, ieache_circuit **out)
 extern "C" void ieache_circuit_destroy(ieache_circuit *c)
 {
     if (!c) return;
-    if (c->d_tmpl) { cudaSetDevice(c->device); cudaFree(c->d_tmpl); }
+    if (c->d_tmpl) { cudaSetDevice(c->device); cudaFree(c->d_tmpl); cudaFree(c->d_out_slots); }
     delete c;
 }
 extern "C" int ieache_circuit_stats(const ieache_circuit *c, uint64_t *bootstraps, uint64_t *and_gates, uint64_t *xor_gates,
@@ -773,13 +785,21 @@ extern "C" int ieache_circuit_stats(const ieache_circuit *c, uint64_t *bootstrap
 static int circuit_upload(ieache_ctx *ctx, ieache_circuit *c)
 {
     if (c->d_tmpl && c->device == ctx->device) return IEACHE_OK;
-    if (c->d_tmpl) { cudaSetDevice(c->device); cudaFree(c->d_tmpl); c->d_tmpl = nullptr; }
+    if (c->d_tmpl) { cudaSetDevice(c->device); cudaFree(c->d_tmpl); cudaFree(c->d_out_slots); c->d_tmpl = nullptr; c->d_out_slots = nullptr; }
     CU(cudaSetDevice(ctx->device));
+    /* output slot table (sign folded: outputs of cloud.c circuits are never negated refs) */
+    std::vector<int32_t> out_slots(c->c.outputs.size());
+    for (size_t i = 0; i < c->c.outputs.size(); i++) {
+        if (c->c.outputs[i].neg) return fail(IEACHE_ERR_UNSUPPORTED, "negated output reference");
+        out_slots[i] = c->c.slot_of_wire[c->c.outputs[i].wire];
+    }
     std::vector<GateT> all;
     c->level_off.clear();
     for (const Level &lv : c->c.levels) { c->level_off.push_back(all.size()); all.insert(all.end(), lv.tmpl.begin(), lv.tmpl.end()); }
     CU(cudaMalloc((void **)&c->d_tmpl, all.size() * sizeof(GateT)));
     CU(cudaMemcpy(c->d_tmpl, all.data(), all.size() * sizeof(GateT), cudaMemcpyHostToDevice));
+    CU(cudaMalloc((void **)&c->d_out_slots, out_slots.size() * 4));
+    CU(cudaMemcpy(c->d_out_slots, out_slots.data(), out_slots.size() * 4, cudaMemcpyHostToDevice));
     c->device = ctx->device;
     return IEACHE_OK;
 }
@@ -800,15 +820,6 @@ extern "C" int ieache_circuit_eval_device(ieache_ctx *ctx, const ieache_cloudkey
     per = std::max<size_t>(1, std::min<size_t>(per, (size_t)(1u << 20) / std::max<uint32_t>(1, C.max_width)));
     if ((rc = ensure(ctx, &ctx->d_wires, &ctx->wires_cap, per * C.n_slots * kLweStride))) return rc;
     if ((rc = ensure(ctx, &ctx->d_ext, &ctx->ext_cap, per * C.max_width * kExtStride))) return rc;
-    /* output slot table (sign folded: outputs of cloud.c circuits are never negated refs) */
-    std::vector<int32_t> out_slots(C.outputs.size());
-    for (size_t i = 0; i < C.outputs.size(); i++) {
-        if (C.outputs[i].neg) return fail(IEACHE_ERR_UNSUPPORTED, "negated output reference");
-        out_slots[i] = C.slot_of_wire[C.outputs[i].wire];
-    }
-    int32_t *d_out_slots = nullptr;
-    CU(cudaMalloc((void **)&d_out_slots, out_slots.size() * 4));
-    CU(cudaMemcpyAsync(d_out_slots, out_slots.data(), out_slots.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     for (size_t off = 0; off < n_expr; off += per) {
         const int m = (int)std::min(per, n_expr - off);
         CU(launch_circuit_scatter_inputs(ctx->d_wires, inputs + off * C.n_inputs * kLweStride, m, C.n_inputs, C.n_slots, n, key->dp.mu, ctx->stream));
@@ -818,15 +829,14 @@ extern "C" int ieache_circuit_eval_device(ieache_ctx *ctx, const ieache_cloudkey
             ga.tmpl = c->d_tmpl + c->level_off[L];
             ga.ntempl = (int)C.levels[L].tmpl.size();
             ga.n_inst = m; ga.inst_samples = C.n_slots; ga.stride = kLweStride;
-            if ((rc = run_br(ctx, key, ga, ctx->d_wires, ctx->d_wires, 0))) { cudaFree(d_out_slots); return rc; }
-            if ((rc = run_ks(ctx, key, ga, ctx->d_wires, 0, 0))) { cudaFree(d_out_slots); return rc; }
+            if ((rc = run_br(ctx, key, ga, ctx->d_wires, ctx->d_wires, 0))) return rc;
+            if ((rc = run_ks(ctx, key, ga, ctx->d_wires, 0, 0))) return rc;
         }
-        CU(launch_circuit_gather_outputs(outputs + off * C.outputs.size() * kLweStride, ctx->d_wires, d_out_slots, m,
+        CU(launch_circuit_gather_outputs(outputs + off * C.outputs.size() * kLweStride, ctx->d_wires, c->d_out_slots, m,
                                          (int)C.outputs.size(), C.n_slots, n, ctx->stream));
         ctx->launches++;
     }
     CU(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_out_slots);
     return IEACHE_OK;
 }
 
@@ -1188,9 +1198,9 @@ extern "C" int ieache_keygen_files(ieache_ctx *ctx, const char *dir, const ieach
         ieache_secretkey *sk = nullptr;
         ieache_cloudkey *ck = nullptr;
         if ((rc = ieache_keygen(ctx, p, which ? seed_nbit : seed_key, &sk, &ck, hk.bk.data(), hk.ksk.data()))) return rc;
+        std::unique_ptr<ieache_secretkey, void (*)(ieache_secretkey *)> skg(sk, ieache_secretkey_destroy);
+        std::unique_ptr<ieache_cloudkey, void (*)(ieache_cloudkey *)> ckg(ck, ieache_cloudkey_destroy);
         ieache_secretkey_export(sk, hk.lwe_key.data(), hk.tlwe_key.data());
-        ieache_secretkey_destroy(sk);
-        ieache_cloudkey_destroy(ck);
         std::string msg;
         if (which == 0) {
             if ((rc = write_keyset((d + "/secret.key").c_str(), hk, true, msg))) return fail(rc, "%s", msg.c_str());   /* keygen.c:39-41 */

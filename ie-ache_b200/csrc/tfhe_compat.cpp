@@ -71,7 +71,19 @@ void unpack(LweSample *s, int n, const int32_t *src) { memcpy(s->a, src, 4 * (si
 void gate(int op, LweSample *result, const LweSample *a, const LweSample *b, const LweSample *c, int32_t imm, int32_t count,
           const TFheGateBootstrappingCloudKeySet *bk)
 {
+    /* libtfhe code sometimes passes &secret_keyset->cloud.  Key sets read from a secret-key file by this layer carry no
+     * bootstrapping key on the device (Cloud/cloud.c only decrypts with nbit.key), and that member is not a CloudWrap:
+     * refuse it by name instead of reinterpreting whatever lies behind it */
+    if (!bk || !bk->bkFFT) {
+        fprintf(stderr, "ieache_b200 (libtfhe-compatible API): this key set holds no bootstrapping key (a secret key set's .cloud "
+                        "member?); load cloud.key with new_tfheGateBootstrappingCloudKeySet_fromFile\n");
+        abort();
+    }
     const CloudWrap *w = cw(bk);
+    if (reinterpret_cast<const LweBootstrappingKeyFFT *>(w->key) != bk->bkFFT) {
+        fprintf(stderr, "ieache_b200 (libtfhe-compatible API): not a cloud key set made by this library\n");
+        abort();
+    }
     const int n = w->params->raw.n;
     const size_t rec = (size_t)n + 1;
     /* cloud.c calls gates from OpenMP sections on a shared key (cloud.c:27-41): the engine context's staging

@@ -31,11 +31,17 @@ def broadcast_params(params, src: int = 0):
     return out
 
 
-def broadcast_cloud_key(engine, key, params, src: int = 0):
-    """One-time replication of the device-resident cloud key: rank `src` owns `key`; every other rank
-    allocates torch CUDA tensors of the same size, receives the transform-domain BK and the packed KSK
-    over NCCL, and wraps them with ieache_cloudkey_adopt_device.  Returns (CloudKey, keepalive)."""
+def broadcast_cloud_key(engine, key, params, src: int = 0, timings: dict | None = None):
+    """One-time replication of the device-resident cloud key: rank `src` owns `key`; every other rank allocates
+    tensors of the same size, receives the transform-domain BK and the packed KSK with two broadcasts (NCCL over
+    NVLink on the GPU box), and wraps them with ieache_cloudkey_adopt_device.  Returns (CloudKey, keepalive).
+
+    `timings` (optional) receives broadcast_ms (device time of the two broadcasts, max over ranks; the communicator is
+    assumed to be up — bench.py times its bring-up separately) and bytes.  Under the gloo backend (CPU tests) the
+    tensors live in host memory and `engine` / `key` may be stand-ins with the same methods: the protocol is the
+    same."""
     import ctypes
+    import time
 
     import torch
     import torch.distributed as dist
@@ -43,12 +49,13 @@ def broadcast_cloud_key(engine, key, params, src: int = 0):
     from . import lib
 
     rank = dist.get_rank()
+    on_gpu = dist.get_backend() == "nccl"
     params = broadcast_params(params, src)
     bkb, ksb = ctypes.c_size_t(), ctypes.c_size_t()
     rc = lib().ieache_cloudkey_device_sizes(ctypes.byref(params), ctypes.byref(bkb), ctypes.byref(ksb))
     if rc:
         raise RuntimeError(lib().ieache_last_error().decode())
-    dev = torch.device("cuda", torch.cuda.current_device())
+    dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
     bk_t = torch.empty(bkb.value // 8, dtype=torch.float64, device=dev)
     ks_t = torch.empty(ksb.value // 4, dtype=torch.int32, device=dev)
     if rank == src:
@@ -56,9 +63,23 @@ def broadcast_cloud_key(engine, key, params, src: int = 0):
         assert bk_bytes == bkb.value and ks_bytes == ksb.value
         engine.device_copy(bk_t.data_ptr(), bk_ptr, bk_bytes)
         engine.device_copy(ks_t.data_ptr(), ks_ptr, ks_bytes)
+    if on_gpu:
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    t0 = time.perf_counter()
     dist.broadcast(bk_t, src=src)
     dist.broadcast(ks_t, src=src)
-    torch.cuda.synchronize()
+    if on_gpu:
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    else:
+        ms = torch.tensor([1e3 * (time.perf_counter() - t0)], dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if timings is not None:
+        timings["broadcast_ms"] = float(ms.item())
+        timings["bytes"] = bkb.value + ksb.value
     if rank == src:
         return key, (bk_t, ks_t)
     return engine.cloud_key_adopt(params, bk_t.data_ptr(), ks_t.data_ptr()), (bk_t, ks_t)

@@ -17,7 +17,10 @@ def test_reference_arm_prints_the_contract_line():
     assert line["higher_is_better"] is True and line["value"] > 0 and line["steps"] == 1
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert line["config"]["workload"].startswith("bootsNAND_batch_2^20")
+    assert line["config"] == {"workload": "bootsNAND_batch_2^20_per_gpu", "gates_per_step_per_gpu": 1 << 20,
+                              "params": "n=630,N=1024,k=1,l=3,Bgbit=7,t=8,basebit=2",
+                              "parallelism": "dp1 (key replicated, no data-path collective)"}
+    assert line["cpu_baseline"]["port_vs_advertised_libtfhe"] > 0
 
 
 def test_reference_arm_other_ranks_exit_quietly():

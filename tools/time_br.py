@@ -21,4 +21,4 @@ for rep in range(4):
     kt = eng.kernel_times(reset=True)
     if rep and (best is None or kt["blind_rotate_ms"] < best["blind_rotate_ms"]): best = kt
 ok = int((sk.decrypt_from_device(do, count) == 1 - (ba & bb)).sum())
-print(f"variant={os.environ.get('IEACHE_BR_VARIANT','default')} count={count} BR={best['blind_rotate_ms']:.2f} ms ({count/best['blind_rotate_ms']*1e3:.0f} gates/s) KS={best['keyswitch_ms']:.2f} ms total={count/(best['blind_rotate_ms']+best['keyswitch_ms'])*1e3:.0f} gates/s correct={ok}/{count}", flush=True)
+print(f"kernels={eng.pick_kernels(key, count)} count={count} BR={best['blind_rotate_ms']:.2f} ms ({count/best['blind_rotate_ms']*1e3:.0f} gates/s) KS={best['keyswitch_ms']:.2f} ms total={count/(best['blind_rotate_ms']+best['keyswitch_ms'])*1e3:.0f} gates/s correct={ok}/{count}", flush=True)
