@@ -27,6 +27,10 @@
 #include <stdlib.h>
 
 
+#ifndef W12_ROUND
+#define W12_ROUND(v) ((int32_t)__double2ll_rn(v)) /* F2I on the conversion pipe: one FP64 issue less per coefficient than the 1.5 * 2^52 trick */
+#endif
+
 namespace ieache {
 
 /* pass-1 twiddles (br_warp.h tw16_pass1) in constant memory: DFMA takes them as c[bank][offset] operands; as literals
@@ -260,19 +264,19 @@ blind_rotate_w12_kernel(DevParams p, const double2 *__restrict__ bkw, GateAddr g
                         const int off = 32 * (h & 15) + 512 * (h >> 4);
                         const int t = t0 + off;
                         const int32_t v = accq[t & (kN - 1)];
-                        cc[h] = (uint32_t)(((t & kN) ? -v : v) - accq[lane + off]) + offset;
+                        cc[h] = ((uint32_t)(((t & kN) ? -v : v) - accq[lane + off]) + offset) >> 1; /* digit fields stay in place (pass16_fwd_from_fields) */
                     }
                     W12_ST32W(t_cc, cc);
                 }
 #pragma unroll 1
                 for (int pp = 0; pp < L; pp++) {
-                    const int shift = 32 - (pp + 1) * Bgbit;
+                    const int sp = w12_field_shift(pp, Bgbit);
                     double xr[16], xi[16];
                     {
                         uint32_t cd[32];
                         if (pp == 0) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                         W12_LD32W(t_cc, cd);
-                        pass16_fwd_from_digits(cd, shift, maskBg, halfBg, xr, xi, w1);
+                        pass16_fwd_from_fields(cd, maskBg << sp, (uint32_t)halfBg << sp, xr, xi, w1);
                     }
                     __syncwarp();                      /* every lane has finished reading the buffer of the previous transform */
                     st16_pass1(buf, lane, xr, xi);
@@ -342,8 +346,8 @@ blind_rotate_w12_kernel(DevParams p, const double2 *__restrict__ bkw, GateAddr g
                 int32_t *accj = acc + j * kN;
 #pragma unroll
                 for (int m = 0; m < 16; m++) {
-                    accj[lane + 32 * m] += round_to_torus(xr[m]);
-                    accj[lane + 32 * m + 512] += round_to_torus(xi[m]);
+                    accj[lane + 32 * m] += W12_ROUND(xr[m]);
+                    accj[lane + 32 * m + 512] += W12_ROUND(xi[m]);
                 }
             }
             __syncwarp();
@@ -379,19 +383,21 @@ cudaError_t launch_blind_rotate_w12(const DevParams &p, const double2 *bkw, cons
     return cudaErrorInvalidValue;
 }
 
-/* key load: the [slot 8][thread 64] layout of bk_fft_kernel -> [slot 16][lane 32] in the w12_slot_to_K order (same
- * values, permuted) */
-__global__ void __launch_bounds__(512) bk_relayout_w12_kernel(const double2 *__restrict__ old, double2 *__restrict__ neu, int npoly)
+/* key load: the [slot 8][thread 64] layout of bk_fft_kernel -> [slot 16][lane 32] in the w12_slot_to_K order; the rows
+ * of gadget digit p also take the factor 2^-sp that the kernel's in-place digit fields carry (an exact scaling) */
+__global__ void __launch_bounds__(512) bk_relayout_w12_kernel(const double2 *__restrict__ old, double2 *__restrict__ neu, int npoly, int l, int Bgbit)
 {
-    const int q = blockIdx.x, idx = threadIdx.x;
+    const int q = blockIdx.x, idx = threadIdx.x;   /* q = ((i kpl + r) 2 + j): digit p = r mod l */
     if (q >= npoly) return;
     const int K = w12_slot_to_K(idx >> 5, idx & 31);
     const int t3 = 8 * (K & 7) + ((K >> 3) & 7), r8 = brev3(K >> 6); /* br_core.h: K = b + 8k' + 64 brev3(r), t3 = 8b + k' */
-    neu[(size_t)q * kHalfN + idx] = old[(size_t)q * kHalfN + r8 * 64 + t3];
+    const double sc = ldexp(1.0, -w12_field_shift((q >> 1) % l, Bgbit));
+    const double2 v = old[(size_t)q * kHalfN + r8 * 64 + t3];
+    neu[(size_t)q * kHalfN + idx] = make_double2(v.x * sc, v.y * sc);
 }
-cudaError_t launch_bk_relayout_w12(const double2 *bkfft, double2 *bkfft_w, int npoly, cudaStream_t s)
+cudaError_t launch_bk_relayout_w12(const double2 *bkfft, double2 *bkfft_w, int npoly, int l, int Bgbit, cudaStream_t s)
 {
-    bk_relayout_w12_kernel<<<npoly, 512, 0, s>>>(bkfft, bkfft_w, npoly);
+    bk_relayout_w12_kernel<<<npoly, 512, 0, s>>>(bkfft, bkfft_w, npoly, l, Bgbit);
     return cudaGetLastError();
 }
 

@@ -100,6 +100,28 @@ IE_HD void pass16_fwd_from_digits(const uint32_t (&cc)[32], int shift, uint32_t 
     }
     pass16_fwd_tail(xr, xi, w);
 }
+/* The same pass from digits that are left IN PLACE in the word: ch[h] = (coefficient + decomposition offset) >> 1, so
+ * digit p sits at bits [sp, sp + Bgbit) with sp = 31 - (p + 1) Bgbit and every sum / difference of two fields fits an
+ * int32.  field = ch & (mask << sp) is the digit times 2^sp: no shift per digit, and the power of two is taken out
+ * again by the key (the rows of digit p are stored times 2^-sp, w12 layout) — scaling by a power of two commutes with
+ * every rounding on the way, so the result is bit-identical to the unscaled transform.
+ * M = mask << sp, H = half << sp. */
+IE_HD void pass16_fwd_from_fields(const uint32_t (&ch)[32], uint32_t M, uint32_t H, double (&xr)[16], double (&xi)[16], const Tw16 &w)
+{
+    const double c = 0.70710678118654752440;
+#pragma unroll
+    for (int m = 0; m < 8; m++) {
+        const int32_t ar_i = (int32_t)((ch[m] & M) - H), ai_i = (int32_t)((ch[16 + m] & M) - H);
+        const uint32_t br_u = ch[m + 8] & M, bi_u = ch[24 + m] & M;
+        const double ar = (double)ar_i, ai = (double)ai_i;
+        const double u = (double)(int32_t)(br_u - bi_u), v = (double)(int32_t)(br_u + bi_u - 2u * H);
+        xr[m] = fma(c, u, ar); xi[m] = fma(c, v, ai);
+        xr[m + 8] = fma(-c, u, ar); xi[m + 8] = fma(-c, v, ai);
+    }
+    pass16_fwd_tail(xr, xi, w);
+}
+/* bit position of digit p in ch, and the factor the key rows of digit p carry */
+IE_HD int w12_field_shift(int p, int Bgbit) { return 31 - (p + 1) * Bgbit; }
 /* inverse pass (x16) */
 IE_HD void pass16_inv(double (&xr)[16], double (&xi)[16], const Tw16 &w)
 {

@@ -542,7 +542,7 @@ static int run_br(ieache_ctx *ctx, const ieache_cloudkey *key, const GateAddr &g
     if (ctx->timing) { CU(cudaEventCreate(&t.a)); CU(cudaEventCreate(&t.b)); t.kind = 0; CU(cudaEventRecord(t.a, ctx->stream)); }
     if (!key->bkfft_w && pick_blind_rotate(ctx->policy, (long long)ga.ntempl * ga.n_inst) == BR_W12) {
         CU(cudaMalloc((void **)&key->bkfft_w, key->bkfft_bytes));
-        CU(launch_bk_relayout_w12(key->bkfft, key->bkfft_w, (int)(key->bkfft_bytes / (kHalfNBytes)), ctx->stream));
+        CU(launch_bk_relayout_w12(key->bkfft, key->bkfft_w, (int)(key->bkfft_bytes / (kHalfNBytes)), key->dp.l, key->dp.Bgbit, ctx->stream));
         ctx->launches++;
     }
     CU(launch_blind_rotate(key->dp, ctx->policy, key->bkfft, key->bkfft_w, ga, A, B, ext ? ext : ctx->d_ext, ext_base, ctx->stream));
@@ -804,8 +804,19 @@ static int circuit_upload(ieache_ctx *ctx, ieache_circuit *c)
     return IEACHE_OK;
 }
 
+/* launches everything on the context's stream and returns without waiting */
+static int circuit_eval_device_async(ieache_ctx *ctx, const ieache_cloudkey *key, const ieache_circuit *cc, const int32_t *inputs,
+                                     int32_t *outputs, size_t n_expr);
 extern "C" int ieache_circuit_eval_device(ieache_ctx *ctx, const ieache_cloudkey *key, const ieache_circuit *cc, const int32_t *inputs,
                                           int32_t *outputs, size_t n_expr)
+{
+    int rc = circuit_eval_device_async(ctx, key, cc, inputs, outputs, n_expr);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return IEACHE_OK;
+}
+static int circuit_eval_device_async(ieache_ctx *ctx, const ieache_cloudkey *key, const ieache_circuit *cc, const int32_t *inputs,
+                                     int32_t *outputs, size_t n_expr)
 {
     if (!ctx || !key || !cc || !inputs || !outputs) return fail(IEACHE_ERR_ARG, "null argument");
     if (n_expr == 0) return IEACHE_OK;
@@ -836,7 +847,6 @@ extern "C" int ieache_circuit_eval_device(ieache_ctx *ctx, const ieache_cloudkey
                                          (int)C.outputs.size(), C.n_slots, n, ctx->stream));
         ctx->launches++;
     }
-    CU(cudaStreamSynchronize(ctx->stream));
     return IEACHE_OK;
 }
 
@@ -923,47 +933,143 @@ extern "C" int ieache_session_params(const ieache_session *s, ieache_params *out
     return IEACHE_OK;
 }
 
+/* ---- operand batches resident on the device -------------------------------------------------------------------
+ * The value part of `count` operand (or answer) blocks: 8 value chunks, least significant first, and the carry block
+ * — 9 blocks of 32 samples each, device stride.  The two metadata blocks (sign code, width) are encrypted under
+ * nbit.key, which the Cloud holds and cloud.c decrypts on the host anyway (cloud.c:709-796): they travel as plain
+ * integers next to the device array and are only encrypted again when an answer leaves the engine. */
+constexpr int kValBlocks = 9;
+constexpr size_t kBlockWords = (size_t)32 * kLweStride;
+struct DevValues {
+    DevBuf buf;
+    size_t count = 0;
+    std::vector<int32_t> sign, width;
+    std::vector<int32_t> exit_code;      /* per element: 0, or 126 once a 256-bit multiply was refused (cloud.c:860-864) */
+    std::vector<uint8_t> computed;       /* per element: a circuit produced the value blocks (352-sample answer) */
+    int32_t *d() const { return buf.as<int32_t>(); }
+    int32_t *block(size_t e, int blk) const { return d() + (e * kValBlocks + blk) * kBlockWords; }
+    int alloc(size_t n)
+    {
+        count = n;
+        sign.assign(n, 0); width.assign(n, 0); exit_code.assign(n, 0); computed.assign(n, 1);
+        if (n == 0) return IEACHE_OK;
+        CU(buf.alloc(n * kValBlocks * kBlockWords * sizeof(int32_t)));
+        return IEACHE_OK;
+    }
+};
+
+/* pinned staging: two slots so that slot k+1 is packed and copied while slot k is in use */
+struct PinnedSlots {
+    int32_t *h[2] = {nullptr, nullptr};
+    size_t words = 0;
+    ~PinnedSlots() { for (int i = 0; i < 2; i++) if (h[i]) cudaFreeHost(h[i]); }
+    int ensure(size_t w)
+    {
+        if (w <= words) return IEACHE_OK;
+        for (int i = 0; i < 2; i++) { if (h[i]) cudaFreeHost(h[i]); h[i] = nullptr; }
+        words = 0;
+        for (int i = 0; i < 2; i++) CU(cudaHostAlloc((void **)&h[i], w * sizeof(int32_t), cudaHostAllocDefault));
+        words = w;
+        return IEACHE_OK;
+    }
+};
+constexpr size_t kSessionChunk = 64; /* requests per pass of the host-buffer calls: bounds pinned memory to
+                                        2 slots x 64 x 9 x 32 x (n + 1) x 4 B = 93 MB at n = 630 (x3: two operands, one answer) */
+
+/* host operand blocks (352 samples of n + 1 words; element e at base + e * stride words) -> device values + metadata */
+static int upload_values(ieache_session *s, size_t count, const int32_t *base, size_t stride_words, DevValues &out, PinnedSlots &pin)
+{
+    ieache_ctx *ctx = s->ctx;
+    const int n = s->key->p.n;
+    const size_t w = n + 1, B = 32 * w, vwords = kValBlocks * B;
+    int rc = out.alloc(count);
+    if (rc) return rc;
+    if ((rc = pin.ensure(kSessionChunk * vwords))) return rc;
+    cudaEvent_t ev[2];
+    for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    size_t chunk = 0;
+    for (size_t off = 0; off < count; off += kSessionChunk, chunk++) {
+        const size_t m = std::min(kSessionChunk, count - off);
+        const int slot = (int)(chunk & 1);
+        if (chunk >= 2) CU(cudaEventSynchronize(ev[slot]));                       /* the copy out of this slot two chunks ago is done */
+        for (size_t e = 0; e < m; e++) {
+            const int32_t *blk = base + (off + e) * stride_words;
+            out.sign[off + e] = dec32(s->nbit, blk);                              /* cloud.c:780-796 */
+            out.width[off + e] = dec32(s->nbit, blk + B);                         /* cloud.c:709-746 */
+            memcpy(pin.h[slot] + e * vwords, blk + 2 * B, vwords * sizeof(int32_t));
+        }
+        CU(cudaMemcpy2DAsync(out.block(off, 0), kLweStride * 4, pin.h[slot], w * 4, w * 4, m * kValBlocks * 32, cudaMemcpyHostToDevice, ctx->h2d_stream));
+        CU(cudaEventRecord(ev[slot], ctx->h2d_stream));
+        ctx->h2d_value_copies += m;
+    }
+    CU(cudaStreamSynchronize(ctx->h2d_stream));
+    for (int i = 0; i < 2; i++) cudaEventDestroy(ev[i]);
+    return IEACHE_OK;
+}
+
+/* device values + metadata -> host answer blocks: sign[32] (nbit key) || width[32] (nbit key) || 8 result blocks || carry
+ * (cloud.c:812-855, 899-916).  answer_counts[e] = 352, or 64 when nothing was computed for the element. */
+static int download_values(ieache_session *s, const DevValues &v, int32_t *answers, size_t stride_words, size_t *answer_counts, PinnedSlots &pin)
+{
+    ieache_ctx *ctx = s->ctx;
+    const int n = s->key->p.n;
+    const size_t w = n + 1, B = 32 * w, vwords = kValBlocks * B;
+    int rc;
+    if ((rc = pin.ensure(kSessionChunk * vwords))) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (size_t off = 0; off < v.count; off += kSessionChunk) {
+        const size_t m = std::min(kSessionChunk, v.count - off);
+        CU(cudaMemcpy2DAsync(pin.h[0], w * 4, v.block(off, 0), kLweStride * 4, w * 4, m * kValBlocks * 32, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        CU(cudaStreamSynchronize(ctx->d2h_stream));
+        ctx->d2h_value_copies += m;
+        for (size_t e = 0; e < m; e++) {
+            int32_t *ans = answers + (off + e) * stride_words;
+            enc32(s->nbit, v.sign[off + e], ans);
+            enc32(s->nbit, v.width[off + e], ans + B);
+            if (v.computed[off + e]) memcpy(ans + 2 * B, pin.h[0] + e * vwords, vwords * sizeof(int32_t));
+            if (answer_counts) answer_counts[off + e] = v.computed[off + e] ? 352 : 64;
+        }
+    }
+    return IEACHE_OK;
+}
+
 struct Request { int kind = 0, width = 0; bool swap = false; };
 
-/* `count` requests (operator + two 352-sample client blocks each) -> `count` answer blocks.
- * Metadata handling is Cloud/cloud.c:709-864 per request; requests that need the same circuit are
- * evaluated together, level by level. exit_codes[i] = 0 or 126; answer_counts[i] = 352 or 64 samples. */
-extern "C" int ieache_session_compute_batch(ieache_session *s, size_t count, const int32_t *ops, const int32_t *operands1,
-                                            const int32_t *operands2, int32_t *answers, int32_t *exit_codes, size_t *answer_counts,
-                                            double *seconds)
+/* One operator over `count` element pairs, everything on the device.  Metadata handling is Cloud/cloud.c:780-864 per
+ * element; elements that need the same circuit are evaluated together, level by level.  R receives the answers
+ * (value blocks on the device, metadata in plain). */
+static int apply_operator(ieache_session *s, const int32_t *ops, const DevValues &A, const DevValues &Bv, DevValues &R, double *seconds)
 {
-    if (!s || !ops || !operands1 || !operands2 || !answers) return fail(IEACHE_ERR_ARG, "null argument");
-    const int n = s->key->p.n;
-    const size_t w = n + 1, B = 32 * w, blk = 352 * w;
+    ieache_ctx *ctx = s->ctx;
+    const size_t count = A.count;
+    int rc = R.alloc(count);
+    if (rc) return rc;
     std::vector<Request> req(count);
-    std::map<std::pair<int, int>, std::vector<size_t>> groups; /* (kind | swap<<8, width) -> request indices */
+    std::map<std::pair<int, int>, std::vector<size_t>> groups; /* (kind | swap<<8, width) -> element indices */
     for (size_t i = 0; i < count; i++) {
-        const int32_t *o1 = operands1 + i * blk, *o2 = operands2 + i * blk;
-        int32_t *ans = answers + i * blk;
         const int int_op = ops[i];
-        const int32_t int_bit1 = dec32(s->nbit, o1 + B), int_bit2 = dec32(s->nbit, o2 + B);   /* cloud.c:709-746 */
-        int32_t n1 = dec32(s->nbit, o1);
-        const int32_t n2 = dec32(s->nbit, o2);                                               /* cloud.c:780-796 */
-        if (n1 == 2) n1 = 1;
+        const int32_t int_bit1 = A.width[i], int_bit2 = Bv.width[i];
+        int32_t n1 = A.sign[i];
+        const int32_t n2 = Bv.sign[i];
+        if (n1 == 2) n1 = 1;                                                                          /* cloud.c:788-789 */
         const int32_t int_negative = n1 + n2;
-        /* cloud.c:812-826: 1 -> 1, 2 -> 2, 3 -> 4, anything else (an operand block that already carries code 4 from an
-         * earlier operator of a chain) -> 0 */
-        enc32(s->nbit, int_negative == 1 ? 1 : int_negative == 2 ? 2 : int_negative == 3 ? 4 : 0, ans);
-        int32_t int_bit;
-        if (int_op == 4) { int_bit = std::max(int_bit1, int_bit2); enc32(s->nbit, int_bit * 2, ans + B); }   /* cloud.c:833-843 */
-        else if (int_bit1 >= int_bit2) { int_bit = int_bit1; memcpy(ans + B, o1 + B, B * 4); }
-        else { int_bit = int_bit2; memcpy(ans + B, o2 + B, B * 4); }
-        if (exit_codes) exit_codes[i] = 0;
-        if (answer_counts) answer_counts[i] = 64;
+        /* cloud.c:812-826: 1 -> 1, 2 -> 2, 3 -> 4, anything else (an operand that already carries code 4 from an earlier
+         * operator of a chain) -> 0 */
+        R.sign[i] = int_negative == 1 ? 1 : int_negative == 2 ? 2 : int_negative == 3 ? 4 : 0;
+        const int32_t int_bit = std::max(int_bit1, int_bit2);
+        R.width[i] = int_op == 4 ? int_bit * 2 : int_bit;                                             /* cloud.c:833-855 */
+        R.exit_code[i] = std::max(A.exit_code[i], Bv.exit_code[i]);
+        R.computed[i] = 0;
         Request &r = req[i];
         r.width = int_bit;
-        if (int_op == 4 && int_bit >= 256) { if (exit_codes) exit_codes[i] = 126; continue; }             /* cloud.c:860-864 */
+        if (R.exit_code[i]) continue;                                                                 /* the chain stopped earlier */
+        if (int_op == 4 && int_bit >= 256) { R.exit_code[i] = 126; continue; }                        /* cloud.c:860-864 */
         if ((int_op == 1 && int_negative != 1 && int_negative != 2) || (int_op == 2 && (int_negative == 1 || int_negative == 2)))
-            r.kind = IEACHE_CIRC_ADD;                                                                    /* cloud.c:870 */
+            r.kind = IEACHE_CIRC_ADD;                                                                 /* cloud.c:870 */
         else if (int_op == 2 || (int_op == 1 && (int_negative == 1 || int_negative == 2))) {
-            r.kind = IEACHE_CIRC_SUB;                                                                    /* cloud.c:1194 */
-            r.swap = !((int_op == 2 && int_negative == 0) || (int_op == 1 && int_negative == 2));        /* cloud.c:1196,1809 */
-        } else if (int_op == 4) r.kind = IEACHE_CIRC_MUL;                                                /* cloud.c:2368 */
+            r.kind = IEACHE_CIRC_SUB;                                                                 /* cloud.c:1194 */
+            r.swap = !((int_op == 2 && int_negative == 0) || (int_op == 1 && int_negative == 2));     /* cloud.c:1196,1809 */
+        } else if (int_op == 4) r.kind = IEACHE_CIRC_MUL;                                             /* cloud.c:2368 */
         if (!r.kind) continue;
         const bool ok_width = (r.kind == IEACHE_CIRC_MUL) ? (int_bit == 32 || int_bit == 64 || int_bit == 128)
                                                           : (int_bit == 32 || int_bit == 64 || int_bit == 128 || int_bit == 256);
@@ -976,29 +1082,73 @@ extern "C" int ieache_session_compute_batch(ieache_session *s, size_t count, con
         const bool swap_ops = (kv.first.first & 256) != 0;
         const std::vector<size_t> &idx = kv.second;
         ieache_circuit *&circ = s->circuits[{kind, width}];
-        int rc;
         if (!circ && (rc = ieache_circuit_build(kind, width, &circ))) return rc;
         const int nc = width / 32;
-        const size_t nin = circ->c.n_inputs, nout = circ->c.outputs.size();
-        std::vector<int32_t> in(idx.size() * nin * w), out(idx.size() * nout * w);
-        for (size_t e = 0; e < idx.size(); e++) {
-            const int32_t *o1 = operands1 + idx[e] * blk, *o2 = operands2 + idx[e] * blk;
-            int32_t *dst = &in[e * nin * w];
-            memcpy(dst, (swap_ops ? o2 : o1) + 2 * B, (size_t)nc * B * 4);
-            memcpy(dst + (size_t)nc * B, (swap_ops ? o1 : o2) + 2 * B, (size_t)nc * B * 4);
-            memcpy(dst + (size_t)2 * nc * B, o1 + 10 * B, B * 4);                 /* ciphertextcarry1 */
+        const size_t nin = circ->c.n_inputs / 32, nout = circ->c.outputs.size() / 32, m = idx.size();   /* in blocks of 32 samples */
+        DevBuf din, dout, dptr;
+        CU(din.alloc(m * nin * kBlockWords * 4));
+        CU(dout.alloc(m * nout * kBlockWords * 4));
+        /* assemble the circuit inputs on the device: [first operand chunks][second operand chunks][operand 1's carry block] */
+        std::vector<const void *> src;
+        std::vector<void *> dst;
+        for (size_t e = 0; e < m; e++) {
+            const size_t i = idx[e];
+            const DevValues &X = swap_ops ? Bv : A, &Y = swap_ops ? A : Bv;
+            int32_t *in = din.as<int32_t>() + e * nin * kBlockWords;
+            for (int c = 0; c < nc; c++) { src.push_back(X.block(i, c)); dst.push_back(in + (size_t)c * kBlockWords); }
+            for (int c = 0; c < nc; c++) { src.push_back(Y.block(i, c)); dst.push_back(in + (size_t)(nc + c) * kBlockWords); }
+            src.push_back(A.block(i, 8)); dst.push_back(in + (size_t)2 * nc * kBlockWords);          /* ciphertextcarry1 */
         }
+        /* and where the results go: result blocks, then copies of operand 1's carry block as padding and as block 10 (cloud.c:899-916) */
+        const size_t n_in_copies = src.size();
+        for (size_t e = 0; e < m; e++) {
+            const size_t i = idx[e];
+            for (size_t q = 0; q < 8; q++) {
+                src.push_back(q < nout ? (const void *)(dout.as<int32_t>() + (e * nout + q) * kBlockWords) : (const void *)A.block(i, 8));
+                dst.push_back(R.block(i, (int)q));
+            }
+            src.push_back(A.block(i, 8)); dst.push_back(R.block(i, 8));
+            R.computed[i] = 1;
+        }
+        CU(dptr.alloc(src.size() * 2 * sizeof(void *)));
+        const void **d_src = dptr.as<const void *>();
+        void **d_dst = reinterpret_cast<void **>(dptr.as<void *>() + src.size());
+        CU(cudaMemcpyAsync(d_src, src.data(), src.size() * sizeof(void *), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(d_dst, dst.data(), dst.size() * sizeof(void *), cudaMemcpyHostToDevice, ctx->stream));
+        CU(launch_copy_blocks(d_src, d_dst, (int)n_in_copies, ctx->stream));
+        ctx->launches++;
         const auto t0 = std::chrono::steady_clock::now();
-        if ((rc = ieache_circuit_eval(s->ctx, s->key, circ, in.data(), out.data(), idx.size()))) return rc;
+        if ((rc = circuit_eval_device_async(ctx, s->key, circ, din.as<int32_t>(), dout.as<int32_t>(), m))) return rc;
+        CU(launch_copy_blocks(d_src + n_in_copies, d_dst + n_in_copies, (int)(src.size() - n_in_copies), ctx->stream));
+        ctx->launches++;
+        CU(cudaStreamSynchronize(ctx->stream));        /* din / dout / dptr are released on leaving the scope */
         secs += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        const size_t nres = nout / 32;
-        for (size_t e = 0; e < idx.size(); e++) {
-            const int32_t *carry1 = operands1 + idx[e] * blk + 10 * B;
-            int32_t *ans = answers + idx[e] * blk;
-            for (size_t q = 0; q < 8; q++) memcpy(ans + (2 + q) * B, q < nres ? &out[(e * nout + q * 32) * w] : carry1, B * 4);   /* cloud.c:899-916 */
-            memcpy(ans + 10 * B, carry1, B * 4);
-            if (answer_counts) answer_counts[idx[e]] = 352;
-        }
+    }
+    if (seconds) *seconds += secs;
+    return IEACHE_OK;
+}
+
+/* `count` requests (operator + two 352-sample client blocks each) -> `count` answer blocks, in passes of kSessionChunk
+ * requests through pinned staging slots (bounded host and device memory whatever `count` is).
+ * exit_codes[i] = 0 or 126; answer_counts[i] = 352 or 64 samples. */
+extern "C" int ieache_session_compute_batch(ieache_session *s, size_t count, const int32_t *ops, const int32_t *operands1,
+                                            const int32_t *operands2, int32_t *answers, int32_t *exit_codes, size_t *answer_counts,
+                                            double *seconds)
+{
+    if (!s || !ops || !operands1 || !operands2 || !answers) return fail(IEACHE_ERR_ARG, "null argument");
+    CU(cudaSetDevice(s->ctx->device));
+    const size_t blk = 352 * (size_t)(s->key->p.n + 1);
+    PinnedSlots pin;
+    double secs = 0;
+    for (size_t off = 0; off < count; off += kSessionChunk) {
+        const size_t m = std::min(kSessionChunk, count - off);
+        DevValues A, B, R;
+        int rc;
+        if ((rc = upload_values(s, m, operands1 + off * blk, blk, A, pin))) return rc;
+        if ((rc = upload_values(s, m, operands2 + off * blk, blk, B, pin))) return rc;
+        if ((rc = apply_operator(s, ops + off, A, B, R, &secs))) return rc;
+        if ((rc = download_values(s, R, answers + off * blk, blk, answer_counts ? answer_counts + off : nullptr, pin))) return rc;
+        if (exit_codes) for (size_t e = 0; e < m; e++) exit_codes[off + e] = R.exit_code[e];
     }
     if (seconds) *seconds = secs;
     return IEACHE_OK;
@@ -1016,58 +1166,75 @@ extern "C" int ieache_session_compute(ieache_session *s, int op, const int32_t *
 /* A whole postfix expression per instance, e.g. "AB*C+" (Output/output_dynamic.py builds it; the Cloud walks
  * it at Cloud/dragonfly_cipher_cloud.py:685-729).  Letters index the operand blocks (A = 0), operators are
  * + - * (opcodes 1, 2, 4).  Operand order follows the infix expression exactly as the reference's `flip`
- * logic does.  All instances share the postfix string; each operator is one batched compute over all
- * instances.  Stops early (returns 126) if any instance hits the 256-bit multiply abort, like the reference. */
+ * logic does.  All instances share the postfix string; each operator is one batched evaluation over all instances of a
+ * pass.  Operands go to the device once, intermediate results STAY there (only their sign code and width, which the
+ * Cloud decrypts anyway, are host integers), and only the final answers come back: n_operands uploads and one download
+ * per instance whatever the number of operators.  Returns 126 if any instance hit the 256-bit multiply abort. */
 extern "C" int ieache_session_eval_postfix(ieache_session *s, const char *postfix, size_t n_expr, const int32_t *operands,
                                            int n_operands, int32_t *answers, size_t *answer_counts, double *seconds)
 {
     if (!s || !postfix || !operands || !answers) return fail(IEACHE_ERR_ARG, "null argument");
-    const size_t w = s->key->p.n + 1, blk = 352 * w;
-    std::vector<std::vector<int32_t>> pool;          /* intermediate results, [n_expr][352][w] each */
-    std::vector<const int32_t *> stack_ptr;           /* base pointer of a stacked value */
-    std::vector<size_t> stack_stride;                 /* distance between instances */
+    if (n_operands < 1 || n_operands > 26) return fail(IEACHE_ERR_ARG, "1..26 operands");
+    CU(cudaSetDevice(s->ctx->device));
+    const size_t blk = 352 * (size_t)(s->key->p.n + 1);
+    /* validate the expression once */
+    {
+        int depth = 0;
+        for (const char *c = postfix; *c; ++c) {
+            if (*c == ' ') continue;
+            if (*c >= 'A' && *c <= 'Z') {
+                if (*c - 'A' >= n_operands) return fail(IEACHE_ERR_ARG, "postfix names operand %c but only %d were given", *c, n_operands);
+                depth++;
+            } else if (*c == '+' || *c == '-' || *c == '*') {
+                if (depth < 2) return fail(IEACHE_ERR_ARG, "malformed postfix expression");
+                depth--;
+            } else return fail(IEACHE_ERR_ARG, "unknown token '%c' in postfix expression", *c);
+        }
+        if (depth < 1) return fail(IEACHE_ERR_ARG, "empty postfix expression");
+    }
+    PinnedSlots pin;
     double secs = 0;
     int last_code = 0;
-    for (const char *c = postfix; *c; ++c) {
-        if (*c == ' ') continue;
-        if (*c >= 'A' && *c <= 'Z') {
-            const int k = *c - 'A';
-            if (k >= n_operands) return fail(IEACHE_ERR_ARG, "postfix names operand %c but only %d were given", *c, n_operands);
-            stack_ptr.push_back(operands + (size_t)k * blk);
-            stack_stride.push_back((size_t)n_operands * blk);
-            continue;
+    for (size_t off = 0; off < n_expr; off += kSessionChunk) {
+        const size_t m = std::min(kSessionChunk, n_expr - off);
+        std::vector<std::unique_ptr<DevValues>> loaded(n_operands);   /* operand k of this pass, uploaded on first use */
+        std::vector<std::unique_ptr<DevValues>> temps;                /* intermediate results */
+        std::vector<DevValues *> stack;
+        int rc;
+        for (const char *c = postfix; *c; ++c) {
+            if (*c == ' ') continue;
+            if (*c >= 'A' && *c <= 'Z') {
+                const int k = *c - 'A';
+                if (!loaded[k]) {
+                    loaded[k].reset(new DevValues());
+                    if ((rc = upload_values(s, m, operands + (off * n_operands + k) * blk, (size_t)n_operands * blk, *loaded[k], pin))) return rc;
+                }
+                stack.push_back(loaded[k].get());
+                continue;
+            }
+            const int32_t op = *c == '+' ? 1 : *c == '-' ? 2 : 4;
+            DevValues *b = stack.back(); stack.pop_back();
+            DevValues *a = stack.back(); stack.pop_back();
+            std::vector<int32_t> ops(m, op);
+            temps.emplace_back(new DevValues());
+            if ((rc = apply_operator(s, ops.data(), *a, *b, *temps.back(), &secs))) return rc;
+            stack.push_back(temps.back().get());
         }
-        const int op = *c == '+' ? 1 : *c == '-' ? 2 : *c == '*' ? 4 : 0;
-        if (!op) return fail(IEACHE_ERR_ARG, "unknown token '%c' in postfix expression", *c);
-        if (stack_ptr.size() < 2) return fail(IEACHE_ERR_ARG, "malformed postfix expression");
-        const int32_t *b = stack_ptr.back(); const size_t bs = stack_stride.back(); stack_ptr.pop_back(); stack_stride.pop_back();
-        const int32_t *a = stack_ptr.back(); const size_t as = stack_stride.back(); stack_ptr.pop_back(); stack_stride.pop_back();
-        std::vector<int32_t> o1(n_expr * blk), o2(n_expr * blk), ops(n_expr, op), codes(n_expr);
-        for (size_t e = 0; e < n_expr; e++) { memcpy(&o1[e * blk], a + e * as, blk * 4); memcpy(&o2[e * blk], b + e * bs, blk * 4); }
-        pool.emplace_back(n_expr * blk);
-        std::vector<size_t> counts(n_expr);
-        double t = 0;
-        int rc = ieache_session_compute_batch(s, n_expr, ops.data(), o1.data(), o2.data(), pool.back().data(), codes.data(), counts.data(), &t);
-        if (rc) return rc;
-        secs += t;
-        for (size_t e = 0; e < n_expr; e++) if (codes[e]) last_code = codes[e];
-        stack_ptr.push_back(pool.back().data());
-        stack_stride.push_back(blk);
-        if (answer_counts) for (size_t e = 0; e < n_expr; e++) answer_counts[e] = counts[e];
-        if (last_code) break;      /* dragonfly_cipher_cloud.py:1295-1297: send the short answer and stop */
+        DevValues *res = stack.back();
+        if ((rc = download_values(s, *res, answers + off * blk, blk, answer_counts ? answer_counts + off : nullptr, pin))) return rc;
+        for (size_t e = 0; e < m; e++) if (res->exit_code[e]) last_code = res->exit_code[e];
     }
-    if (stack_ptr.empty()) return fail(IEACHE_ERR_ARG, "empty postfix expression");
-    for (size_t e = 0; e < n_expr; e++) memcpy(answers + e * blk, stack_ptr.back() + e * stack_stride.back(), blk * 4);
     if (seconds) *seconds = secs;
     return last_code;
 }
 
 /* Batched ingest: `count` request directories, each holding what ./cloud reads (cloud.data =
- * two 352-record client blocks, operator.txt), evaluated as ONE levelised batch with the session's keys; every
+ * two 352-record client blocks, operator.txt), evaluated as levelised batches with the session's keys; every
  * directory gets the answer.data (and, on multiply, the averagestandard.txt line) ./cloud would have written.
- * Files are parsed and written by a small pool of host threads; the circuit time is shared by all requests of a
- * group, so `seconds` is the time of the whole batch.  exit_codes[i] = 0 / 126 like ./cloud, or a negative
- * IEACHE_ERR_* when that directory could not be read or written (the others still run). */
+ * Directories are taken in passes of kSessionChunk: files are parsed and written by a small pool of host threads, the
+ * requests of a pass form one batch, and host memory stays bounded by the pass size whatever `count` is.  `seconds` is
+ * the circuit time of the whole call.  exit_codes[i] = 0 / 126 like ./cloud, or a negative IEACHE_ERR_* when that
+ * directory could not be read or written (the others still run). */
 extern "C" int ieache_session_compute_dirs(ieache_session *s, size_t count, const char *const *dirs, int32_t *exit_codes, double *seconds)
 {
     if (!s || !dirs || !exit_codes) return fail(IEACHE_ERR_ARG, "null argument");
@@ -1075,54 +1242,59 @@ extern "C" int ieache_session_compute_dirs(ieache_session *s, size_t count, cons
     if (count == 0) return IEACHE_OK;
     const int n = s->key->p.n;
     const size_t w = n + 1, blk = 352 * w;
-    std::vector<int32_t> o1(count * blk), o2(count * blk), answers(count * blk), ops(count, 0), codes(count, 0);
-    std::vector<size_t> counts(count, 0);
-    std::vector<int> io_err(count, 0);
     const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-    auto parallel = [&](auto &&fn) {
-        std::vector<std::thread> pool;
-        std::atomic<size_t> next{0};
-        for (unsigned t = 0; t < std::min<size_t>(hw, count); t++)
-            pool.emplace_back([&] { for (size_t i; (i = next.fetch_add(1)) < count;) fn(i); });
-        for (auto &th : pool) th.join();
-    };
-    parallel([&](size_t i) {
-        const std::string d(dirs[i] ? dirs[i] : "");
-        std::vector<int32_t> data(704 * w);
-        FILE *f = fopen((d + "/cloud.data").c_str(), "rb");
-        if (!f) { io_err[i] = IEACHE_ERR_IO; return; }
-        const int rc = read_samples(f, n, data.data(), 704);
-        fclose(f);
-        if (rc) { io_err[i] = rc; return; }
-        memcpy(&o1[i * blk], data.data(), blk * 4);
-        memcpy(&o2[i * blk], data.data() + blk, blk * 4);
-        int op = 0;
-        f = fopen((d + "/operator.txt").c_str(), "r");
-        if (!f) { io_err[i] = IEACHE_ERR_IO; return; }
-        if (fscanf(f, "%d", &op) != 1) op = 0;
-        fclose(f);
-        ops[i] = op;
-    });
-    /* unreadable directories are left out of the batch (operator 0 selects no circuit, cloud.c computes nothing) */
-    for (size_t i = 0; i < count; i++) if (io_err[i]) ops[i] = 0;
-    double secs = 0;
-    const int rc = ieache_session_compute_batch(s, count, ops.data(), o1.data(), o2.data(), answers.data(), codes.data(), counts.data(), &secs);
-    if (rc) return rc;
-    const double var = s->key->p.ks_stdev * s->key->p.ks_stdev;
-    parallel([&](size_t i) {
-        if (io_err[i]) { exit_codes[i] = io_err[i]; return; }
-        exit_codes[i] = codes[i];
-        const std::string d(dirs[i]);
-        if (counts[i] == 352 && ops[i] == 4) {                                   /* cloud.c:2468-2471 */
-            FILE *t = fopen((d + "/averagestandard.txt").c_str(), "a");
-            if (t) { fprintf(t, "%lf\n", secs); fclose(t); }
-        }
-        FILE *f = fopen((d + "/answer.data").c_str(), "wb");
-        if (!f) { exit_codes[i] = IEACHE_ERR_IO; return; }
-        if (write_samples(f, n, &answers[i * blk], counts[i], var)) exit_codes[i] = IEACHE_ERR_IO;
-        fclose(f);
-    });
-    if (seconds) *seconds = secs;
+    double total = 0;
+    for (size_t off = 0; off < count; off += kSessionChunk) {
+        const size_t m = std::min(kSessionChunk, count - off);
+        std::vector<int32_t> o1(m * blk), o2(m * blk), answers(m * blk), ops(m, 0), codes(m, 0);
+        std::vector<size_t> counts(m, 0);
+        std::vector<int> io_err(m, 0);
+        auto parallel = [&](auto &&fn) {
+            std::vector<std::thread> pool;
+            std::atomic<size_t> next{0};
+            for (unsigned t = 0; t < std::min<size_t>(hw, m); t++)
+                pool.emplace_back([&] { for (size_t i; (i = next.fetch_add(1)) < m;) fn(i); });
+            for (auto &th : pool) th.join();
+        };
+        parallel([&](size_t i) {
+            const std::string d(dirs[off + i] ? dirs[off + i] : "");
+            std::vector<int32_t> data(704 * w);
+            FILE *f = fopen((d + "/cloud.data").c_str(), "rb");
+            if (!f) { io_err[i] = IEACHE_ERR_IO; return; }
+            const int rc = read_samples(f, n, data.data(), 704);
+            fclose(f);
+            if (rc) { io_err[i] = rc; return; }
+            memcpy(&o1[i * blk], data.data(), blk * 4);
+            memcpy(&o2[i * blk], data.data() + blk, blk * 4);
+            int op = 0;
+            f = fopen((d + "/operator.txt").c_str(), "r");
+            if (!f) { io_err[i] = IEACHE_ERR_IO; return; }
+            if (fscanf(f, "%d", &op) != 1) op = 0;
+            fclose(f);
+            ops[i] = op;
+        });
+        /* unreadable directories are left out of the batch (operator 0 selects no circuit, cloud.c computes nothing) */
+        for (size_t i = 0; i < m; i++) if (io_err[i]) ops[i] = 0;
+        double secs = 0;
+        const int rc = ieache_session_compute_batch(s, m, ops.data(), o1.data(), o2.data(), answers.data(), codes.data(), counts.data(), &secs);
+        if (rc) return rc;
+        total += secs;
+        const double var = s->key->p.ks_stdev * s->key->p.ks_stdev;
+        parallel([&](size_t i) {
+            if (io_err[i]) { exit_codes[off + i] = io_err[i]; return; }
+            exit_codes[off + i] = codes[i];
+            const std::string d(dirs[off + i]);
+            if (counts[i] == 352 && ops[i] == 4) {                                   /* cloud.c:2468-2471 */
+                FILE *t = fopen((d + "/averagestandard.txt").c_str(), "a");
+                if (t) { fprintf(t, "%lf\n", secs); fclose(t); }
+            }
+            FILE *f = fopen((d + "/answer.data").c_str(), "wb");
+            if (!f) { exit_codes[off + i] = IEACHE_ERR_IO; return; }
+            if (write_samples(f, n, &answers[i * blk], counts[i], var)) exit_codes[off + i] = IEACHE_ERR_IO;
+            if (fclose(f) != 0) exit_codes[off + i] = IEACHE_ERR_IO;
+        });
+    }
+    if (seconds) *seconds = total;
     return IEACHE_OK;
 }
 

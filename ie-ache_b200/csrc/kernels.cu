@@ -1076,6 +1076,26 @@ cudaError_t launch_circuit_gather_outputs(int32_t *outputs, const int32_t *wires
     return cudaGetLastError();
 }
 
+/* ------------------------------------------------------------------ operand blocks of the session layer */
+/* copies `nblocks` blocks of 32 samples (32 x kLweStride words) between device arrays: src[b] / dst[b] are absolute
+ * device addresses.  Used to assemble circuit inputs from, and to place circuit outputs into, the device-resident
+ * operand batches of engine.cu (the splice Cloud/dragonfly_cipher_cloud.py:1306-1315 does on files). */
+__global__ void __launch_bounds__(256) copy_blocks_kernel(const int4 *const *__restrict__ src, int4 *const *__restrict__ dst, int nblocks)
+{
+    const int b = blockIdx.x;
+    if (b >= nblocks) return;
+    const int4 *s = src[b];
+    int4 *d = dst[b];
+    constexpr int kVec = 32 * kLweStride / 4;
+    for (int i = threadIdx.x; i < kVec; i += 256) d[i] = s[i];
+}
+cudaError_t launch_copy_blocks(const void *const *d_src, void *const *d_dst, int nblocks, cudaStream_t s)
+{
+    if (nblocks <= 0) return cudaSuccess;
+    copy_blocks_kernel<<<nblocks, 256, 0, s>>>(reinterpret_cast<const int4 *const *>(d_src), reinterpret_cast<int4 *const *>(d_dst), nblocks);
+    return cudaGetLastError();
+}
+
 /* ------------------------------------------------------------------ FP64 pipe peak (roofline denominator) */
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters)
 {

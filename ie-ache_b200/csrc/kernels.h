@@ -78,7 +78,7 @@ cudaError_t launch_blind_rotate(const DevParams &p, const LaunchPolicy &pol, con
 cudaError_t upload_twiddles_w12();
 cudaError_t launch_blind_rotate_w12(const DevParams &p, const double2 *bkfft_w, const GateAddr &ga, const int32_t *baseA,
                                     const int32_t *baseB, int32_t *ext, long long count, int sms, cudaStream_t s);
-cudaError_t launch_bk_relayout_w12(const double2 *bkfft, double2 *bkfft_w, int npoly, cudaStream_t s);
+cudaError_t launch_bk_relayout_w12(const double2 *bkfft, double2 *bkfft_w, int npoly, int l, int Bgbit, cudaStream_t s);
 /* key switch of ext[g] (+ ext[g + pair_offset] if pair_offset > 0) + (0, cst_post) into sample out of out_base */
 cudaError_t launch_keyswitch(const DevParams &p, const LaunchPolicy &pol, const int32_t *ksk, const GateAddr &ga, int32_t *out_base,
                              const int32_t *ext, int pair_offset, int32_t cst_post, cudaStream_t s);
@@ -94,6 +94,9 @@ cudaError_t launch_circuit_scatter_inputs(int32_t *wires, const int32_t *inputs,
                                           int32_t mu, cudaStream_t s);
 cudaError_t launch_circuit_gather_outputs(int32_t *outputs, const int32_t *wires, const int32_t *out_slots, int n_expr,
                                           int n_outputs, int n_slots, int n, cudaStream_t s);
+
+/* session layer: copy blocks of 32 samples between device arrays given as arrays of device addresses */
+cudaError_t launch_copy_blocks(const void *const *d_src, void *const *d_dst, int nblocks, cudaStream_t s);
 
 /* dense FP64 FMA microbenchmark (best of 3), TFLOP/s */
 cudaError_t launch_fp64_peak(cudaStream_t s, double *tflops);

@@ -427,9 +427,11 @@ void emul_w12f_blind_rotate(int n, int l, int Bgbit, int32_t mu, const int32_t *
         for (long q = 0; q < (long)n * kpl * 2; q++) {
             emul_poly_fft(bk_coef + (size_t)q * kN, old.data(), 1.0 / 512.0);
             double *dst = &bkw[(size_t)q * 1024];
+            const int dig = (int)((q / 2) % l);                       /* q = ((i kpl + r) 2 + j), digit p = r mod l */
+            const double sc = ldexp(1.0, -w12_field_shift(dig, Bgbit));   /* rows of digit p carry 2^-sp (pass16_fwd_from_fields) */
             for (int p = 0; p < 16; p++) for (int lane = 0; lane < 32; lane++) {
                 const int src = pos_of_K[w12_slot_to_K(p, lane)];
-                dst[2 * (p * 32 + lane)] = old[2 * src]; dst[2 * (p * 32 + lane) + 1] = old[2 * src + 1];
+                dst[2 * (p * 32 + lane)] = old[2 * src] * sc; dst[2 * (p * 32 + lane) + 1] = old[2 * src + 1] * sc;
             }
         }
     }
@@ -460,11 +462,11 @@ void emul_w12f_blind_rotate(int n, int l, int Bgbit, int32_t mu, const int32_t *
             for (int lane = 0; lane < 32; lane++) {
                 int32_t c[32];
                 rot_minus_one32(&acc[q * kN], lane, a, c);
-                for (int h = 0; h < 32; h++) cc[lane][h] = (uint32_t)c[h] + offset;
+                for (int h = 0; h < 32; h++) cc[lane][h] = ((uint32_t)c[h] + offset) >> 1;
             }
             for (int pp = 0; pp < l; pp++) {
-                const int shift = 32 - (pp + 1) * Bgbit;
-                for (int lane = 0; lane < 32; lane++) { pass16_fwd_from_digits(cc[lane], shift, maskBg, halfBg, t[lane].xr, t[lane].xi, e.w1); st16_pass1(buf, lane, t[lane].xr, t[lane].xi); }
+                const int sp = w12_field_shift(pp, Bgbit);
+                for (int lane = 0; lane < 32; lane++) { pass16_fwd_from_fields(cc[lane], maskBg << sp, (uint32_t)halfBg << sp, t[lane].xr, t[lane].xi, e.w1); st16_pass1(buf, lane, t[lane].xr, t[lane].xi); }
                 for (int lane = 0; lane < 32; lane++) { ld16_pass2(buf, lane, t[lane].xr, t[lane].xi); pass16_fwd_g(t[lane].xr, t[lane].xi, e.w2[lane]); }
                 double ssr[32][8], ssi[32][8];
                 for (int lane = 0; lane < 32; lane++) for (int s8 = 0; s8 < 8; s8++) { ssr[lane][s8] = t[lane].xr[8 + s8]; ssi[lane][s8] = t[lane].xi[8 + s8]; }

@@ -111,3 +111,64 @@ def test_cloud_dynamic_mirror(tmp_path, pkg, oracle, env):
     code, w, chunks = oracle.verif(ks, nbit, ks.read_samples(os.path.join(d, "answer.data"), 352))
     assert w == 64 and chunks[0] | (chunks[1] << 32) == 1000 * 2000 + 3000
     node.close()
+
+
+def test_chained_operators_keep_values_on_the_device(oracle, env):
+    """SURVEY 8 f-1: in a postfix expression every operand goes to the GPU once and only the final answers come back;
+    intermediate results never visit the host (the context counts the 352-sample blocks the session calls copy).
+    Five operators over four operands, 70 instances (two passes of 64): 4 x 70 uploads, 70 downloads."""
+    eng, ks, nbit, sess = env
+    n_expr = 70
+    rng = np.random.default_rng(70)
+    vals = rng.integers(1, 1 << 12, size=(n_expr, 4))
+    ops = np.stack([np.stack([oracle.alice(ks, nbit, 0, 32, int(v), seed=100 * e + k) for k, v in enumerate(t)]) for e, t in enumerate(vals)])
+    h0, d0 = eng.copy_counts()
+    rc, ans, counts, _ = sess.eval_postfix("AB+C+D+A-B+", ops)
+    h1, d1 = eng.copy_counts()
+    assert rc == 0 and (counts == 352).all()
+    assert (h1 - h0, d1 - d0) == (4 * n_expr, n_expr)
+    for e, (a, b, c, d) in enumerate(vals):
+        code, w, chunks = oracle.verif(ks, nbit, ans[e])
+        assert ob.decode_result(1, code, w, chunks) == int(a + b + c + d - a + b), e
+
+
+def test_sign_code_of_a_chained_product_of_negatives(oracle, env):
+    """(-a) * (-b) carries sign code 4; added to c the reference writes code 0 for the sum 4 + 0 (cloud.c:812-821) and runs
+    the add branch: the chained session must do what the reference's cloud.c does with that operand block"""
+    eng, ks, nbit, sess = env
+    a, b, c = 1234, 77, 99
+    ops = np.stack([oracle.alice(ks, nbit, 2, 32, a, seed=1), oracle.alice(ks, nbit, 2, 32, b, seed=2), oracle.alice(ks, nbit, 0, 32, c, seed=3)])[None]
+    rc, ans, counts, _ = sess.eval_postfix("AB*C+", ops)
+    assert rc == 0
+    _, prod = oracle.cloud_main(ks, nbit, 4, np.concatenate([ops[0, 0], ops[0, 1]]))
+    assert oracle.verif(ks, nbit, prod)[0] == 4
+    _, want = oracle.cloud_main(ks, nbit, 1, np.concatenate([prod, ops[0, 2]]))
+    assert oracle.verif(ks, nbit, ans[0]) == oracle.verif(ks, nbit, want)
+    assert oracle.verif(ks, nbit, ans[0])[0] == 0
+
+
+def test_ingest_of_many_request_directories_in_bounded_passes(tmp_path, pkg, oracle, env):
+    """SURVEY 8 f-4 at a size that needs several passes: 150 request directories (3 passes of 64) through
+    compute_dirs; host and pinned memory are bounded by the pass size, not by the number of directories"""
+    eng, ks, nbit, _ = env
+    keys = str(tmp_path / "keys")
+    os.makedirs(keys)
+    ks.write_cloud_key(os.path.join(keys, "cloud.key"))
+    nbit.write_secret_key(os.path.join(keys, "nbit.key"))
+    sess = eng.session(os.path.join(keys, "cloud.key"), os.path.join(keys, "nbit.key"))
+    dirs, want = [], []
+    for k in range(150):
+        d = str(tmp_path / f"r{k}")
+        os.makedirs(d)
+        op = (1, 2, 1)[k % 3]
+        a, b = 1000 + 7 * k, 3 * k + 1
+        data = np.concatenate([oracle.alice(ks, nbit, 0, 32, a, seed=2 * k), oracle.alice(ks, nbit, 0, 32, b, seed=2 * k + 1)])
+        ks.write_samples(data, os.path.join(d, "cloud.data"))
+        open(os.path.join(d, "operator.txt"), "w").write(str(op))
+        dirs.append(d); want.append(a + b if op == 1 else a - b)
+    codes, secs = sess.compute_dirs(dirs)
+    assert (codes == 0).all() and secs > 0
+    for d, k in zip(dirs, range(150)):
+        code, w, chunks = oracle.verif(ks, nbit, ks.read_samples(os.path.join(d, "answer.data"), 352))
+        assert ob.decode_result((1, 2, 1)[k % 3], code, w, chunks) == want[k], k
+    sess.close()

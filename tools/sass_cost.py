@@ -6,7 +6,9 @@ IMAD/MOV each hold a sub-partition's dispatch port for two cycles.  This script 
 `cuobjdump -sass` output (backward branches), prints the instruction mix of each and the cost of one step for given
 trip counts, so that a restructuring can be judged before GPU time is spent.
 
-usage: sass_cost.py <object-or-so> <kernel-name-regex> [weights, e.g. 6,2,2 in order of loop start address]
+usage: sass_cost.py <object-or-so> <kernel-name-regex> [weights in order of loop start address, e.g. 0,0,1,2,6,2 | auto]
+       auto: warp-per-gate kernel structure — the loop with most DFMA is the forward transform (x6 per CMux step), the
+       one with most DADD the inverse (x2), the forward's parent the per-polynomial loop (x2), their parent the step (x1)
 """
 import collections, re, subprocess, sys
 
@@ -30,7 +32,8 @@ def opcode(txt):
 
 def main():
     path, pat = sys.argv[1], sys.argv[2]
-    weights = [float(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else None
+    auto = len(sys.argv) > 3 and sys.argv[3] == "auto"
+    weights = [float(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 and not auto else None
     for name, ins in kernels(path).items():
         if not re.search(pat, name): continue
         print(name, len(ins), "instructions")
@@ -42,6 +45,21 @@ def main():
                     tgt = int(hexes[-1], 16)
                     if tgt <= addr: loops.append((tgt, addr))
         loops.sort()
+        if auto:
+            def own(lo, hi):
+                inner = [(a, b) for (a, b) in loops if a >= lo and b <= hi and (a, b) != (lo, hi)]
+                return collections.Counter(opcode(t).split(".")[0] for a, t in ins if lo <= a <= hi and not any(x <= a <= y for x, y in inner))
+            counts = [own(lo, hi) for lo, hi in loops]
+            fwd = max(range(len(loops)), key=lambda k: counts[k]["DFMA"])
+            inv = max(range(len(loops)), key=lambda k: counts[k]["DADD"])
+            parent = lambda k: min((j for j in range(len(loops)) if j != k and loops[j][0] <= loops[k][0] and loops[j][1] >= loops[k][1]),
+                                   key=lambda j: loops[j][1] - loops[j][0], default=None)
+            q = parent(fwd)
+            step = parent(inv)
+            weights = [0.0] * len(loops)
+            weights[fwd] = 6.0; weights[inv] = 2.0
+            if q is not None: weights[q] = 2.0
+            if step is not None: weights[step] = 1.0
         total = 0.0
         for k, (lo, hi) in enumerate(loops):
             inner = [(a, b) for (a, b) in loops if a >= lo and b <= hi and (a, b) != (lo, hi)]
