@@ -27,6 +27,15 @@
 #include <stdlib.h>
 
 
+#ifndef W12_INV_DIT
+#define W12_INV_DIT 1
+#endif
+#ifndef W12_ATOMS
+#define W12_ATOMS 1
+#endif
+#ifndef W12_ROT_ASM
+#define W12_ROT_ASM 1
+#endif
 #ifndef W12_ROUND
 #define W12_ROUND(v) ((int32_t)__double2ll_rn(v)) /* F2I on the conversion pipe: one FP64 issue less per coefficient than the 1.5 * 2^52 trick */
 #endif
@@ -35,6 +44,8 @@ namespace ieache {
 
 /* pass-1 twiddles (br_warp.h tw16_pass1) in constant memory: DFMA takes them as c[bank][offset] operands; as literals
  * the compiler rebuilt every one of them in uniform registers inside the loop (62 UMOV per transform) */
+__constant__ TwInvP1 c12_inv1 = IE_TW_INV_P1_INIT;
+__constant__ int c12_m1 = -1; /* a run-time -1: keeps "offset - x" on the multiply-add pipe */
 __constant__ Tw16 c12_w1 = {0.70710678118654752440, 0.70710678118654752440, 0.92387953251128675613, 0.38268343236508977173,
                             0.98078528040323044913, 0.19509032201612826785, 0.55557023301960222474, 0.83146961230254523708,
                             0.99518472667219688624, 0.09801714032956060199, 0.63439328416364549822, 0.77301045336273696081,
@@ -102,6 +113,64 @@ __device__ __forceinline__ uint32_t smem_u32_w12(const void *p) { return (uint32
     "tcgen05.st.sync.aligned.32x32b.x4.b32 [%0 + 12], {t12,t13,t14,t15};\n\t}" \
     :: "r"(taddr), "d"(d[0]),"d"(d[1]),"d"(d[2]),"d"(d[3]),"d"(d[4]),"d"(d[5]),"d"(d[6]),"d"(d[7]) : "memory")
 
+#ifndef W12_TM2
+#define W12_TM2 1
+#endif
+#if W12_TM2
+/* ... and as eight 2-register accesses: a double is an aligned register pair wherever it lives, so the accumulate has
+ * no placement constraint at all (with quads ptxas still moved 60-110 registers per transform between the load, the
+ * two dependent FMAs and the store); 32 more tensor-memory instructions per transform, each a single issue slot */
+#undef W12_LD4x4
+#undef W12_ST4x4
+#define W12_LD4x4(taddr, d) asm volatile("{\n\t.reg .b32 t<16>;\n\t" \
+    "tcgen05.ld.sync.aligned.32x32b.x2.b32 {t0,t1}, [%8];\n\t" \
+    "tcgen05.ld.sync.aligned.32x32b.x2.b32 {t2,t3}, [%8 + 2];\n\t" \
+    "tcgen05.ld.sync.aligned.32x32b.x2.b32 {t4,t5}, [%8 + 4];\n\t" \
+    "tcgen05.ld.sync.aligned.32x32b.x2.b32 {t6,t7}, [%8 + 6];\n\t" \
+    "tcgen05.ld.sync.aligned.32x32b.x2.b32 {t8,t9}, [%8 + 8];\n\t" \
+    "tcgen05.ld.sync.aligned.32x32b.x2.b32 {t10,t11}, [%8 + 10];\n\t" \
+    "tcgen05.ld.sync.aligned.32x32b.x2.b32 {t12,t13}, [%8 + 12];\n\t" \
+    "tcgen05.ld.sync.aligned.32x32b.x2.b32 {t14,t15}, [%8 + 14];\n\t" \
+    "tcgen05.wait::ld.sync.aligned;\n\t" \
+    "mov.b64 %0, {t0,t1};\n\tmov.b64 %1, {t2,t3};\n\tmov.b64 %2, {t4,t5};\n\tmov.b64 %3, {t6,t7};\n\tmov.b64 %4, {t8,t9};\n\tmov.b64 %5, {t10,t11};\n\tmov.b64 %6, {t12,t13};\n\tmov.b64 %7, {t14,t15};\n\t}" \
+    : "=d"(d[0]),"=d"(d[1]),"=d"(d[2]),"=d"(d[3]),"=d"(d[4]),"=d"(d[5]),"=d"(d[6]),"=d"(d[7]) : "r"(taddr) : "memory")
+#define W12_ST4x4(taddr, d) asm volatile("{\n\t.reg .b32 t<16>;\n\t" \
+    "mov.b64 {t0,t1}, %1;\n\tmov.b64 {t2,t3}, %2;\n\tmov.b64 {t4,t5}, %3;\n\tmov.b64 {t6,t7}, %4;\n\tmov.b64 {t8,t9}, %5;\n\tmov.b64 {t10,t11}, %6;\n\tmov.b64 {t12,t13}, %7;\n\tmov.b64 {t14,t15}, %8;\n\t" \
+    "tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {t0,t1};\n\t" \
+    "tcgen05.st.sync.aligned.32x32b.x2.b32 [%0 + 2], {t2,t3};\n\t" \
+    "tcgen05.st.sync.aligned.32x32b.x2.b32 [%0 + 4], {t4,t5};\n\t" \
+    "tcgen05.st.sync.aligned.32x32b.x2.b32 [%0 + 6], {t6,t7};\n\t" \
+    "tcgen05.st.sync.aligned.32x32b.x2.b32 [%0 + 8], {t8,t9};\n\t" \
+    "tcgen05.st.sync.aligned.32x32b.x2.b32 [%0 + 10], {t10,t11};\n\t" \
+    "tcgen05.st.sync.aligned.32x32b.x2.b32 [%0 + 12], {t12,t13};\n\t" \
+    "tcgen05.st.sync.aligned.32x32b.x2.b32 [%0 + 14], {t14,t15};\n\t" \
+    "}" \
+    :: "r"(taddr), "d"(d[0]),"d"(d[1]),"d"(d[2]),"d"(d[3]),"d"(d[4]),"d"(d[5]),"d"(d[6]),"d"(d[7]) : "memory")
+#endif
+
+/* one coefficient of the rotated difference, halved with the decomposition offset added:
+ * cc = (sign * ACC[(j - a) mod N] - ACC[j] + offset) >> 1 */
+#define W12_ROT(out, aR, aJ, lim, offs, sN, sW, m1, OFF) asm volatile("{\n\t.reg .pred p;\n\t.reg .s32 v, u;\n\t" \
+    "setp.le.s32 p, %3, %8;\n\t" \
+    "@!p ld.shared.s32 v, [%1 + %9];\n\t" \
+    "@p ld.shared.s32 v, [%1 + %10];\n\t" \
+    "ld.shared.s32 u, [%2 + %9];\n\t" \
+    "mad.lo.s32 u, u, %7, %4;\n\t" \
+    "@!p mad.lo.s32 u, v, %5, u;\n\t" \
+    "@p mad.lo.s32 u, v, %6, u;\n\t" \
+    "shr.u32 %0, u, 1;\n\t}" \
+    : "=r"(out) : "r"(aR), "r"(aJ), "r"(lim), "r"(offs), "r"(sN), "r"(sW), "r"(m1), "n"(OFF), "n"(4 * (OFF)), "n"(4 * (OFF) - 4 * kN) : "memory")
+
+template <int H>
+__device__ __forceinline__ void w12_rot_all(uint32_t (&cc)[32], uint32_t aR, uint32_t aJ, int lim, uint32_t offs, int sN, int sW, int m1)
+{
+    if constexpr (H < 32) {
+        constexpr int off = 32 * (H & 15) + 512 * (H >> 4);
+        W12_ROT(cc[H], aR, aJ, lim, offs, sN, sW, m1, off);
+        w12_rot_all<H + 1>(cc, aR, aJ, lim, offs, sN, sW, m1);
+    }
+}
+
 __device__ __forceinline__ double2 ldg_nc_pinned(const double2 *p)
 {
     double2 v;
@@ -162,6 +231,96 @@ __device__ __forceinline__ void w12_load_tw2(Tw16g &w, uint32_t t_tw2, const dou
     w.z2ar = tw[4]; w.z2ai = tw[5]; w.z2br = tw[6]; w.z2bi = tw[7];
     w.z1ar = tw[8]; w.z1ai = tw[9]; w.z1aqr = tw[10]; w.z1aqi = tw[11];
     w.z1br = tw[12]; w.z1bi = tw[13]; w.z1bqr = tw[14]; w.z1bqi = tw[15];
+}
+
+#ifndef W12_NOINLINE
+#define W12_NOINLINE 1
+#endif
+#if W12_NOINLINE
+#define W12_PHASE __device__ __noinline__
+#else
+#define W12_PHASE __device__ __forceinline__
+#endif
+/* phase 1 of a CMux step: cc = ((X^a - 1) ACC_q + offset) >> 1 for the lane's 32 coefficients.  The phases are separate
+ * functions so that each gets its own register allocation: inlined, a change in one phase reshuffles the register quads
+ * of the forward transform and costs it up to 90 register moves */
+W12_PHASE void w12_rotate(const int32_t *acc, int q, int a, int lane, uint32_t offset, uint32_t t_cc)
+{
+    uint32_t cc[32];
+#if W12_ROT_ASM
+    /* coefficient j = lane + off of (X^a - 1) ACC_q: the rotated source sits at R0 + off, wrapped once the
+     * sum reaches N — so both candidate addresses are "register + immediate" and one compare picks the load
+     * and the sign.  IMAD issues at full rate, the INT32 ALU at half rate: the sign is a multiply-add */
+    const uint32_t sa = smem_u32_w12(acc) + (uint32_t)q * (kN * 4);
+    int aq = a;
+    asm volatile("" : "+r"(aq)); /* recomputed per polynomial: nothing of this stays live across the transforms */
+    const int t0 = (lane - aq) & (2 * kN - 1);
+    const int r0 = t0 & (kN - 1);
+    const int sN = (t0 & kN) ? -1 : 1, sW = -sN;
+    const int lim = kN - r0;
+    const uint32_t aR = sa + 4u * (uint32_t)r0, aJ = sa + 4u * (uint32_t)lane;
+    w12_rot_all<0>(cc, aR, aJ, lim, offset, sN, sW, c12_m1);
+#else
+    const int32_t *accq = acc + q * kN;
+    int aq = a;
+    asm volatile("" : "+r"(aq));
+    const int t0 = lane - aq;
+#pragma unroll
+    for (int h = 0; h < 32; h++) {
+        const int off = 32 * (h & 15) + 512 * (h >> 4);
+        const int t = t0 + off;
+        const int32_t v = accq[t & (kN - 1)];
+        cc[h] = ((uint32_t)(((t & kN) ? -v : v) - accq[lane + off]) + offset) >> 1;
+    }
+#endif
+    W12_ST32W(t_cc, cc);   /* digit fields stay in place (pass16_fwd_from_fields); read back once per digit */
+}
+
+/* phase 3: inverse transforms of both accumulator polynomials (which leaves them zero) and the ACC update */
+W12_PHASE void w12_inverse(int32_t *acc, cd *buf, const double2 *s_tab, uint32_t t_acc, uint32_t t_tw2, int lane)
+{
+    const Tw16 &w1 = c12_w1;
+    /* inverse transforms and ACC update */
+#pragma unroll 1
+    for (int j = 0; j < 2; j++) {
+        double xr[16], xi[16];
+        {
+            double s0[16], s1[16];
+            W12_LD16D(t_acc + (uint32_t)(j * 64), s0);
+            W12_LD16D(t_acc + (uint32_t)(j * 64 + 32), s1);
+#pragma unroll
+            for (int r = 0; r < 8; r++) { xr[r] = s0[2 * r]; xi[r] = s0[2 * r + 1]; xr[8 + r] = s1[2 * r]; xi[8 + r] = s1[2 * r + 1]; }
+        }
+#pragma unroll
+        for (int c16 = 0; c16 < 4; c16++) W12_ST_ZERO16(t_acc + (uint32_t)(j * 64 + 16 * c16));
+        w12_fin_inv_half<0>(xr, xi, lane, s_tab);
+        w12_fin_inv_half<1>(xr, xi, lane, s_tab);
+        {
+            Tw16g w2;
+            w12_load_tw2(w2, t_tw2, s_tab, lane);
+            pass16_inv_g(xr, xi, w2);
+        }
+        __syncwarp();
+        st16_ipass2(buf, lane, xr, xi);
+        __syncwarp();
+        ld16_ipass1(buf, lane, xr, xi);
+#if W12_INV_DIT
+        pass16_inv_p1(xr, xi, c12_inv1);
+#else
+        pass16_inv(xr, xi, w1);
+#endif
+        int32_t *accj = acc + j * kN;
+#pragma unroll
+        for (int m = 0; m < 16; m++) {
+#if W12_ATOMS
+            atomicAdd(&accj[lane + 32 * m], W12_ROUND(xr[m]));
+            atomicAdd(&accj[lane + 32 * m + 512], W12_ROUND(xi[m]));
+#else
+            accj[lane + 32 * m] += W12_ROUND(xr[m]);
+            accj[lane + 32 * m + 512] += W12_ROUND(xi[m]);
+#endif
+        }
+    }
 }
 
 template <int L>
@@ -253,21 +412,7 @@ blind_rotate_w12_kernel(DevParams p, const double2 *__restrict__ bkw, GateAddr g
             const double2 *bk_r = bkw + (size_t)i * kBkStride + lane;
 #pragma unroll 1
             for (int q = 0; q < 2; q++) {
-                uint32_t cc[32];
-                {
-                    const int32_t *accq = acc + q * kN;
-                    int aq = a;
-                    asm volatile("" : "+r"(aq)); /* keeps the 32 rotated indices out of registers between the two polynomials */
-                    const int t0 = lane - aq;
-#pragma unroll
-                    for (int h = 0; h < 32; h++) {
-                        const int off = 32 * (h & 15) + 512 * (h >> 4);
-                        const int t = t0 + off;
-                        const int32_t v = accq[t & (kN - 1)];
-                        cc[h] = ((uint32_t)(((t & kN) ? -v : v) - accq[lane + off]) + offset) >> 1; /* digit fields stay in place (pass16_fwd_from_fields) */
-                    }
-                    W12_ST32W(t_cc, cc);
-                }
+                w12_rotate(acc, q, a, lane, offset, t_cc);
 #pragma unroll 1
                 for (int pp = 0; pp < L; pp++) {
                     const int sp = w12_field_shift(pp, Bgbit);
@@ -318,38 +463,7 @@ blind_rotate_w12_kernel(DevParams p, const double2 *__restrict__ bkw, GateAddr g
                 }
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            /* inverse transforms and ACC update */
-#pragma unroll 1
-            for (int j = 0; j < 2; j++) {
-                double xr[16], xi[16];
-                {
-                    double s0[16], s1[16];
-                    W12_LD16D(t_acc + (uint32_t)(j * 64), s0);
-                    W12_LD16D(t_acc + (uint32_t)(j * 64 + 32), s1);
-#pragma unroll
-                    for (int r = 0; r < 8; r++) { xr[r] = s0[2 * r]; xi[r] = s0[2 * r + 1]; xr[8 + r] = s1[2 * r]; xi[8 + r] = s1[2 * r + 1]; }
-                }
-#pragma unroll
-                for (int c16 = 0; c16 < 4; c16++) W12_ST_ZERO16(t_acc + (uint32_t)(j * 64 + 16 * c16));
-                w12_fin_inv_half<0>(xr, xi, lane, s_tab);
-                w12_fin_inv_half<1>(xr, xi, lane, s_tab);
-                {
-                    Tw16g w2;
-                    w12_load_tw2(w2, t_tw2, s_tab, lane);
-                    pass16_inv_g(xr, xi, w2);
-                }
-                __syncwarp();
-                st16_ipass2(buf, lane, xr, xi);
-                __syncwarp();
-                ld16_ipass1(buf, lane, xr, xi);
-                pass16_inv(xr, xi, w1);
-                int32_t *accj = acc + j * kN;
-#pragma unroll
-                for (int m = 0; m < 16; m++) {
-                    accj[lane + 32 * m] += W12_ROUND(xr[m]);
-                    accj[lane + 32 * m + 512] += W12_ROUND(xi[m]);
-                }
-            }
+            w12_inverse(acc, buf, s_tab, t_acc, t_tw2, lane);
             __syncwarp();
         }
 

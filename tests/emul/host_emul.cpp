@@ -42,6 +42,7 @@ struct Emul {
 const Emul &emul() { static Emul e; return e; }
 } // namespace
 
+static const TwInvP1 inv1 = IE_TW_INV_P1_INIT;
 extern "C" {
 
 /* forward transform of one int32 polynomial into the device BK layout [r][t3] (re,im), scaled */
@@ -506,7 +507,7 @@ void emul_w12f_blind_rotate(int n, int l, int Bgbit, int32_t mu, const int32_t *
                 }
             for (int lane = 0; lane < 32; lane++) for (int s8 = 0; s8 < 8; s8++) { t[lane].xr[8 + s8] = ssr[lane ^ 16][s8]; t[lane].xi[8 + s8] = ssi[lane ^ 16][s8]; }
             for (int lane = 0; lane < 32; lane++) { pass16_inv_g(t[lane].xr, t[lane].xi, e.w2[lane]); st16_ipass2(buf, lane, t[lane].xr, t[lane].xi); }
-            for (int lane = 0; lane < 32; lane++) { ld16_ipass1(buf, lane, t[lane].xr, t[lane].xi); pass16_inv(t[lane].xr, t[lane].xi, e.w1); }
+            for (int lane = 0; lane < 32; lane++) { ld16_ipass1(buf, lane, t[lane].xr, t[lane].xi); pass16_inv_p1(t[lane].xr, t[lane].xi, inv1); /* as the kernel: 6-FMA butterflies + one final twist */ }
             for (int lane = 0; lane < 32; lane++)
                 for (int m = 0; m < 16; m++) {
                     acc[j * kN + lane + 32 * m] += round_to_torus(t[lane].xr[m]);
