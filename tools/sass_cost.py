@@ -1,8 +1,9 @@
 """Developer aid: static dispatch-cost estimate of a blind-rotation kernel from its SASS.
 
 Measured on B200 (profiles/README.md, round 2): with 12 resident warps per SM the warp-per-gate kernel runs at
-sum(2 x half-rate instructions + 1 x other instructions) / 4 cycles per CMux step — FP64, the INT32 ALU ops and
-IMAD/MOV each hold a sub-partition's dispatch port for two cycles.  This script finds the loops of a kernel in
+sum(2.2 x FP64 + 2 x other half-rate instructions + 1 x the rest) / 4 cycles per CMux step — FP64, the INT32 ALU ops
+and IMAD/MOV each hold a sub-partition's dispatch port for two cycles (FP64 2.1-2.3 by operand pattern).  Code reached
+through CALL (the phase functions of br_w12.cu) is only counted where it contains a loop.  This script finds the loops of a kernel in
 `cuobjdump -sass` output (backward branches), prints the instruction mix of each and the cost of one step for given
 trip counts, so that a restructuring can be judged before GPU time is spent.
 
@@ -66,7 +67,7 @@ def main():
             body = [(a, t) for a, t in ins if lo <= a <= hi and not any(x <= a <= y for x, y in inner)]
             c = collections.Counter(opcode(t).split(".")[0] for a, t in body)
             half = sum(v for o, v in c.items() if o in HALF)
-            cost = 2 * half + (len(body) - half)
+            cost = 2 * half + (len(body) - half) + 0.2 * sum(v for o, v in c.items() if o in ("DFMA", "DADD", "DMUL"))  # FP64: 2.2 (tools/dfma_probe.cu)
             w = weights[k] if weights and k < len(weights) else 0
             total += w * cost
             top = ", ".join(f"{o}:{v}" for o, v in c.most_common(14))
