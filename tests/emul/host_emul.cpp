@@ -518,4 +518,15 @@ void emul_w12f_blind_rotate(int n, int l, int Bgbit, int32_t mu, const int32_t *
     for (int j = 0; j < kN; j++) ext[j] = (j == 0) ? acc[0] : -acc[kN - j];
     ext[kN] = acc[kN];
 }
+/* the two forms of the last inverse pass (br_warp.h): mirrored butterflies with conj(z) factors, and 6-FMA butterflies
+ * with the pending factors applied at the end */
+void emul_pass16_inv_both(const double *in /*32*/, double *out_mirror /*32*/, double *out_pending /*32*/)
+{
+    double ar[16], ai[16], br[16], bi[16];
+    for (int m = 0; m < 16; m++) { ar[m] = br[m] = in[2 * m]; ai[m] = bi[m] = in[2 * m + 1]; }
+    pass16_inv(ar, ai, tw16_pass1());
+    pass16_inv_p1(br, bi, inv1);
+    for (int m = 0; m < 16; m++) { out_mirror[2 * m] = ar[m]; out_mirror[2 * m + 1] = ai[m]; out_pending[2 * m] = br[m]; out_pending[2 * m + 1] = bi[m]; }
+}
 } // extern "C"
+

@@ -203,3 +203,18 @@ def test_warp_folded_forward_equals_plain_after_key_factor(emul):
     emul.emul_warp_fft(vp(a), vp(plain), ctypes.c_double(1.0))
     emul.emul_warpf_fft_unfolded(vp(a), vp(folded))
     assert np.abs(plain - folded).max() < 1e-9
+
+
+def test_last_inverse_pass_with_pending_factors_equals_mirrored_butterflies(emul):
+    """pass16_inv_p1 (6-FMA butterflies, exp(-i pi pos/32) applied once at the end) is the same linear map as
+    pass16_inv with the pass-1 twiddles: equal to a few ulp of the largest input on 52-bit-sized data."""
+    import ctypes
+    rng = np.random.default_rng(5)
+    f = emul.emul_pass16_inv_both
+    f.argtypes = [ctypes.c_void_p] * 3
+    for scale in (1.0, 2.0 ** 40):
+        x = (rng.standard_normal(32) * scale).astype(np.float64)
+        a = np.zeros(32); b = np.zeros(32)
+        f(x.ctypes.data, a.ctypes.data, b.ctypes.data)
+        assert np.max(np.abs(a)) > 0
+        assert np.max(np.abs(a - b)) <= 64 * np.finfo(np.float64).eps * np.max(np.abs(a))
