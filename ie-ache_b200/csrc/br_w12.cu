@@ -279,7 +279,9 @@ W12_PHASE void w12_rotate(const int32_t *acc, int q, int a, int lane, uint32_t o
 /* phase 3: inverse transforms of both accumulator polynomials (which leaves them zero) and the ACC update */
 W12_PHASE void w12_inverse(int32_t *acc, cd *buf, const double2 *s_tab, uint32_t t_acc, uint32_t t_tw2, int lane)
 {
+#if !W12_INV_DIT
     const Tw16 &w1 = c12_w1;
+#endif
     /* inverse transforms and ACC update */
 #pragma unroll 1
     for (int j = 0; j < 2; j++) {
