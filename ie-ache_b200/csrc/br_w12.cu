@@ -2,10 +2,11 @@
  * br_w12.cu — persistent warp-per-gate blind rotation: 12 gates resident per SM.
  *
  * Same arithmetic as the other blind-rotation kernels (replaces libtfhe's tfhe_blindRotate_FFT /
- * tGswFFTExternMulToTLwe reached from Cloud/cloud.c:30-43), laid out for the unit that bounds the
- * 64-thread kernel: the LSU data pipe.  One WARP owns one gate with 16 points per lane (br_warp.h): a transform
- * needs one shared-memory exchange and one shuffle stage instead of two shared-memory exchanges, and nothing in
- * the CMux loop crosses a warp.  What makes 12 warps fit on an SM (the 64-thread kernel holds 8) is tensor memory:
+ * tGswFFTExternMulToTLwe reached from Cloud/cloud.c:30-43), laid out for what bounds it on this
+ * part: instruction issue — three warps per scheduler instead of two, and as few instructions next to
+ * the FP64 work as the layout allows.  One WARP owns one gate with 16 points per lane (br_warp.h): a transform needs
+ * one shared-memory exchange and one shuffle stage instead of two shared-memory exchanges, and nothing in the CMux
+ * loop crosses a warp.  What makes 12 warps fit on an SM (the 64-thread kernel holds 8) is tensor memory:
  *
  *   TMEM columns (per 32-lane quadrant)   [160 s, 160 s + 128)        transform-domain accumulators of warp slot s = warp / 4
  *                                         [160 s + 128, 160 s + 160)  the 32 rotated differences (X^a - 1) ACC_q of the lane
@@ -26,7 +27,10 @@
 
 #include <stdlib.h>
 
-
+/* Compile-time switches of the A/B measurements in DESIGN.md 4.3 (tools/w12_variants.sh builds one library per
+ * combination; the shipped library is the defaults): W12_TM2 pair-wise (1) or quad (0) tensor-memory accumulate,
+ * W12_NOINLINE phases as functions, W12_ROT_ASM select-free rotation, W12_INV_DIT 6-FMA last inverse pass,
+ * W12_ATOMS shared-memory atomic ACC update. */
 #ifndef W12_INV_DIT
 #define W12_INV_DIT 1
 #endif
