@@ -110,6 +110,7 @@ def lib() -> ctypes.CDLL:
     L.ieache_session_compute_batch.argtypes = [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_double)]
     L.ieache_session_eval_postfix.argtypes = [c_void_p, c_char_p, c_size_t, c_void_p, c_int, c_void_p, c_void_p, POINTER(c_double)]
     L.ieache_session_compute_dirs.argtypes = [c_void_p, c_size_t, c_void_p, c_void_p, POINTER(c_double)]
+    L.ieache_session_set_pass.argtypes = [c_void_p, c_size_t, c_void_p]
     L.ieache_keygen_files.argtypes = [c_void_p, c_char_p, POINTER(Params), c_uint64, c_uint64]
     L.ieache_alice_encrypt.argtypes = [c_char_p, c_int32, c_int32, c_void_p, c_char_p, c_int]
     L.ieache_alice_run.argtypes = [c_char_p]
@@ -294,6 +295,12 @@ class Session:
         secs = c_double()
         _check(lib().ieache_session_compute_dirs(self._h, n, arr, _ptr(codes), byref(secs)))
         return codes, secs.value
+
+    def set_pass(self, requests: int) -> int:
+        """requests evaluated together by the batch calls (default 256); returns the previous value"""
+        old = ctypes.c_size_t()
+        _check(lib().ieache_session_set_pass(self._h, requests, byref(old)))
+        return old.value
 
     def close(self):
         if self._h:

@@ -892,6 +892,7 @@ struct ieache_session {
     bool owns_key = false;
     HostKeySet nbit;
     std::map<std::pair<int, int>, ieache_circuit *> circuits;
+    size_t pass = 256;   /* requests evaluated together by the batch calls (ieache_session_set_pass) */
 };
 
 extern "C" void ieache_session_close(ieache_session *s)
@@ -973,8 +974,20 @@ struct PinnedSlots {
         return IEACHE_OK;
     }
 };
-constexpr size_t kSessionChunk = 64; /* requests per pass of the host-buffer calls: bounds pinned memory to
-                                        2 slots x 64 x 9 x 32 x (n + 1) x 4 B = 93 MB at n = 630 (x3: two operands, one answer) */
+constexpr size_t kSessionChunk = 64; /* operands per staging copy: bounds pinned memory to 2 slots x 64 x 9 x 32 x (n + 1) x 4 B
+                                        = 93 MB at n = 630 whatever the pass size */
+
+/* Requests evaluated together by compute_batch / eval_postfix / compute_dirs.  A pass is what fills the GPU: a 32-bit add
+ * has one or two gates per level, so 256 requests give levels of a few hundred gates and 2 048 reach the persistent
+ * kernel; host memory of compute_dirs is 5.3 MB and device memory 2.2 MB per request of a pass. */
+extern "C" int ieache_session_set_pass(ieache_session *s, size_t requests, size_t *old_value)
+{
+    if (!s) return fail(IEACHE_ERR_ARG, "null session");
+    if (old_value) *old_value = s->pass;
+    if (requests < 1 || requests > 65536) return fail(IEACHE_ERR_ARG, "pass size must be 1..65536 requests");
+    s->pass = requests;
+    return IEACHE_OK;
+}
 
 /* host operand blocks (352 samples of n + 1 words; element e at base + e * stride words) -> device values + metadata */
 static int upload_values(ieache_session *s, size_t count, const int32_t *base, size_t stride_words, DevValues &out, PinnedSlots &pin)
@@ -1128,8 +1141,8 @@ static int apply_operator(ieache_session *s, const int32_t *ops, const DevValues
     return IEACHE_OK;
 }
 
-/* `count` requests (operator + two 352-sample client blocks each) -> `count` answer blocks, in passes of kSessionChunk
- * requests through pinned staging slots (bounded host and device memory whatever `count` is).
+/* `count` requests (operator + two 352-sample client blocks each) -> `count` answer blocks, in passes of s->pass
+ * requests through pinned staging slots (bounded pinned and device memory whatever `count` is).
  * exit_codes[i] = 0 or 126; answer_counts[i] = 352 or 64 samples. */
 extern "C" int ieache_session_compute_batch(ieache_session *s, size_t count, const int32_t *ops, const int32_t *operands1,
                                             const int32_t *operands2, int32_t *answers, int32_t *exit_codes, size_t *answer_counts,
@@ -1140,8 +1153,8 @@ extern "C" int ieache_session_compute_batch(ieache_session *s, size_t count, con
     const size_t blk = 352 * (size_t)(s->key->p.n + 1);
     PinnedSlots pin;
     double secs = 0;
-    for (size_t off = 0; off < count; off += kSessionChunk) {
-        const size_t m = std::min(kSessionChunk, count - off);
+    for (size_t off = 0; off < count; off += s->pass) {
+        const size_t m = std::min(s->pass, count - off);
         DevValues A, B, R;
         int rc;
         if ((rc = upload_values(s, m, operands1 + off * blk, blk, A, pin))) return rc;
@@ -1195,8 +1208,8 @@ extern "C" int ieache_session_eval_postfix(ieache_session *s, const char *postfi
     PinnedSlots pin;
     double secs = 0;
     int last_code = 0;
-    for (size_t off = 0; off < n_expr; off += kSessionChunk) {
-        const size_t m = std::min(kSessionChunk, n_expr - off);
+    for (size_t off = 0; off < n_expr; off += s->pass) {
+        const size_t m = std::min(s->pass, n_expr - off);
         std::vector<std::unique_ptr<DevValues>> loaded(n_operands);   /* operand k of this pass, uploaded on first use */
         std::vector<std::unique_ptr<DevValues>> temps;                /* intermediate results */
         std::vector<DevValues *> stack;
@@ -1231,69 +1244,94 @@ extern "C" int ieache_session_eval_postfix(ieache_session *s, const char *postfi
 /* Batched ingest: `count` request directories, each holding what ./cloud reads (cloud.data =
  * two 352-record client blocks, operator.txt), evaluated as levelised batches with the session's keys; every
  * directory gets the answer.data (and, on multiply, the averagestandard.txt line) ./cloud would have written.
- * Directories are taken in passes of kSessionChunk: files are parsed and written by a small pool of host threads, the
- * requests of a pass form one batch, and host memory stays bounded by the pass size whatever `count` is.  `seconds` is
- * the circuit time of the whole call.  exit_codes[i] = 0 / 126 like ./cloud, or a negative IEACHE_ERR_* when that
- * directory could not be read or written (the others still run). */
+ * Directories are taken in passes of s->pass: files are parsed and written by a small pool of host threads, the
+ * requests of a pass form one batch, and host memory stays bounded by the pass size whatever `count` is.  The files of
+ * pass k + 1 are read and the answers of pass k - 1 written while pass k is on the GPU.  `seconds` is the circuit time of
+ * the whole call.  exit_codes[i] = 0 / 126 like ./cloud, or a negative IEACHE_ERR_* when that directory could not be
+ * read or written (the others still run). */
+namespace {
+struct DirPassIn { size_t off = 0, m = 0; std::vector<int32_t> o1, o2, ops; std::vector<int> io_err; };
+struct DirPassOut { size_t off = 0, m = 0; std::vector<int32_t> answers, codes, ops; std::vector<size_t> counts; std::vector<int> io_err; double secs = 0; };
+template <class Fn> void dir_pool(size_t m, Fn &&fn)
+{
+    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> pool;
+    std::atomic<size_t> next{0};
+    for (unsigned t = 0; t < std::min<size_t>(hw, m); t++)
+        pool.emplace_back([&] { for (size_t i; (i = next.fetch_add(1)) < m;) fn(i); });
+    for (auto &th : pool) th.join();
+}
+} // namespace
 extern "C" int ieache_session_compute_dirs(ieache_session *s, size_t count, const char *const *dirs, int32_t *exit_codes, double *seconds)
 {
     if (!s || !dirs || !exit_codes) return fail(IEACHE_ERR_ARG, "null argument");
     if (seconds) *seconds = 0;
     if (count == 0) return IEACHE_OK;
     const int n = s->key->p.n;
-    const size_t w = n + 1, blk = 352 * w;
-    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-    double total = 0;
-    for (size_t off = 0; off < count; off += kSessionChunk) {
-        const size_t m = std::min(kSessionChunk, count - off);
-        std::vector<int32_t> o1(m * blk), o2(m * blk), answers(m * blk), ops(m, 0), codes(m, 0);
-        std::vector<size_t> counts(m, 0);
-        std::vector<int> io_err(m, 0);
-        auto parallel = [&](auto &&fn) {
-            std::vector<std::thread> pool;
-            std::atomic<size_t> next{0};
-            for (unsigned t = 0; t < std::min<size_t>(hw, m); t++)
-                pool.emplace_back([&] { for (size_t i; (i = next.fetch_add(1)) < m;) fn(i); });
-            for (auto &th : pool) th.join();
-        };
-        parallel([&](size_t i) {
+    const size_t w = n + 1, blk = 352 * w, pass = s->pass;
+    const double var = s->key->p.ks_stdev * s->key->p.ks_stdev;
+    auto read_pass = [&](DirPassIn &in, size_t off) {
+        in.off = off; in.m = std::min(pass, count - off);
+        in.o1.resize(in.m * blk); in.o2.resize(in.m * blk); in.ops.assign(in.m, 0); in.io_err.assign(in.m, 0);
+        dir_pool(in.m, [&](size_t i) {
             const std::string d(dirs[off + i] ? dirs[off + i] : "");
             std::vector<int32_t> data(704 * w);
             FILE *f = fopen((d + "/cloud.data").c_str(), "rb");
-            if (!f) { io_err[i] = IEACHE_ERR_IO; return; }
+            if (!f) { in.io_err[i] = IEACHE_ERR_IO; return; }
             const int rc = read_samples(f, n, data.data(), 704);
             fclose(f);
-            if (rc) { io_err[i] = rc; return; }
-            memcpy(&o1[i * blk], data.data(), blk * 4);
-            memcpy(&o2[i * blk], data.data() + blk, blk * 4);
+            if (rc) { in.io_err[i] = rc; return; }
+            memcpy(&in.o1[i * blk], data.data(), blk * 4);
+            memcpy(&in.o2[i * blk], data.data() + blk, blk * 4);
             int op = 0;
             f = fopen((d + "/operator.txt").c_str(), "r");
-            if (!f) { io_err[i] = IEACHE_ERR_IO; return; }
+            if (!f) { in.io_err[i] = IEACHE_ERR_IO; return; }
             if (fscanf(f, "%d", &op) != 1) op = 0;
             fclose(f);
-            ops[i] = op;
+            in.ops[i] = op;
         });
         /* unreadable directories are left out of the batch (operator 0 selects no circuit, cloud.c computes nothing) */
-        for (size_t i = 0; i < m; i++) if (io_err[i]) ops[i] = 0;
-        double secs = 0;
-        const int rc = ieache_session_compute_batch(s, m, ops.data(), o1.data(), o2.data(), answers.data(), codes.data(), counts.data(), &secs);
-        if (rc) return rc;
-        total += secs;
-        const double var = s->key->p.ks_stdev * s->key->p.ks_stdev;
-        parallel([&](size_t i) {
-            if (io_err[i]) { exit_codes[off + i] = io_err[i]; return; }
-            exit_codes[off + i] = codes[i];
-            const std::string d(dirs[off + i]);
-            if (counts[i] == 352 && ops[i] == 4) {                                   /* cloud.c:2468-2471 */
+        for (size_t i = 0; i < in.m; i++) if (in.io_err[i]) in.ops[i] = 0;
+    };
+    auto write_pass = [&](DirPassOut &out) {
+        dir_pool(out.m, [&](size_t i) {
+            if (out.io_err[i]) { exit_codes[out.off + i] = out.io_err[i]; return; }
+            exit_codes[out.off + i] = out.codes[i];
+            const std::string d(dirs[out.off + i]);
+            if (out.counts[i] == 352 && out.ops[i] == 4) {                           /* cloud.c:2468-2471 */
                 FILE *t = fopen((d + "/averagestandard.txt").c_str(), "a");
-                if (t) { fprintf(t, "%lf\n", secs); fclose(t); }
+                if (t) { fprintf(t, "%lf\n", out.secs); fclose(t); }
             }
             FILE *f = fopen((d + "/answer.data").c_str(), "wb");
-            if (!f) { exit_codes[off + i] = IEACHE_ERR_IO; return; }
-            if (write_samples(f, n, &answers[i * blk], counts[i], var)) exit_codes[off + i] = IEACHE_ERR_IO;
-            if (fclose(f) != 0) exit_codes[off + i] = IEACHE_ERR_IO;
+            if (!f) { exit_codes[out.off + i] = IEACHE_ERR_IO; return; }
+            if (write_samples(f, n, &out.answers[i * blk], out.counts[i], var)) exit_codes[out.off + i] = IEACHE_ERR_IO;
+            if (fclose(f) != 0) exit_codes[out.off + i] = IEACHE_ERR_IO;
         });
+    };
+    DirPassIn in[2];
+    DirPassOut out[2];
+    std::thread reader, writer;
+    auto join = [](std::thread &t) { if (t.joinable()) t.join(); };
+    double total = 0;
+    int rc = IEACHE_OK;
+    read_pass(in[0], 0);
+    size_t k = 0;
+    for (size_t off = 0; off < count; off += pass, k++) {
+        DirPassIn &cur = in[k & 1];
+        DirPassOut &res = out[k & 1];
+        if (off + pass < count) reader = std::thread([&, off] { read_pass(in[(k + 1) & 1], off + pass); });
+        res.off = cur.off; res.m = cur.m; res.ops = cur.ops; res.io_err = cur.io_err;
+        res.answers.resize(cur.m * blk); res.codes.assign(cur.m, 0); res.counts.assign(cur.m, 0); res.secs = 0;
+        rc = ieache_session_compute_batch(s, cur.m, cur.ops.data(), cur.o1.data(), cur.o2.data(), res.answers.data(), res.codes.data(),
+                                          res.counts.data(), &res.secs);
+        join(writer);                 /* the previous pass's answers are on disk before its buffers are reused two passes on */
+        join(reader);
+        if (rc) break;
+        total += res.secs;
+        writer = std::thread([&write_pass, &res] { write_pass(res); });
     }
+    join(reader); join(writer);
+    if (rc) return rc;
     if (seconds) *seconds = total;
     return IEACHE_OK;
 }

@@ -166,6 +166,7 @@ def test_ingest_of_many_request_directories_in_bounded_passes(tmp_path, pkg, ora
         ks.write_samples(data, os.path.join(d, "cloud.data"))
         open(os.path.join(d, "operator.txt"), "w").write(str(op))
         dirs.append(d); want.append(a + b if op == 1 else a - b)
+    assert sess.set_pass(64) == 256               # default pass size; 64 makes this three passes with read-ahead / write-behind
     codes, secs = sess.compute_dirs(dirs)
     assert (codes == 0).all() and secs > 0
     for d, k in zip(dirs, range(150)):
