@@ -78,7 +78,9 @@ def test_batched_ingest_of_request_directories(tmp_path, pkg):
 # ------------------------------------------------------------------ the reference's own cloud.c on this library
 REF_B200 = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "cloud_ref_b200")
 REF_CASES = [(1, 0, 0, 32, 1 << 30, 1 << 30), (1, 2, 2, 32, 5, 7), (2, 0, 0, 32, 1, 1000), (1, 2, 0, 32, 50, 20),
-             (2, 0, 0, 64, (1 << 63) + 5, (1 << 62) + 77), (4, 2, 0, 32, 77777, 99999)]
+             (2, 0, 0, 64, (1 << 63) + 5, (1 << 62) + 77), (4, 2, 0, 32, 77777, 99999),
+             # the wide multipliers through the reference's own main(): 2 x mul64 + split, and 4 x mul128 + 15 chained adds
+             (4, 0, 0, 64, (1 << 62) + 3, (1 << 61) + 5), (4, 0, 2, 128, (1 << 127) - 1, (1 << 126) + 987654321)]
 
 
 @pytest.mark.skipif(not os.path.exists(REF_B200), reason="oracle/_ref/cloud_ref_b200 not built (needs /root/reference at build time)")
