@@ -280,6 +280,22 @@ def test_large_batch_truth_table(pkg, eng):
     key.close(); sk.close()
 
 
+@pytest.mark.parametrize("count", [13, 149, 590, 1000, 1789])
+def test_every_kernel_shape_is_deterministic_run_to_run(pkg, eng, full, count):
+    """The same batch evaluated twice must give the same ciphertext words, for every kernel shape the default policy picks
+    (13 -> 2-CTA cluster, 149 -> pair, 590 -> one gate per CTA, 1000 and the ragged 1789 -> persistent kernel, whose
+    warps exchange data through shared and tensor memory with warp-level synchronisation only).  A missing barrier or an
+    access outside a warp's own buffers shows up as words that differ between runs; this pool offers no race checker, so
+    this and the bit-equality with the integer reference are the evidence."""
+    ks, key = full
+    rng = np.random.default_rng(count)
+    a = ks.encrypt(rng.integers(0, 2, count).astype(np.int32), 11)
+    b = ks.encrypt(rng.integers(0, 2, count).astype(np.int32), 12)
+    first = eng.gate_batch(key, "NAND", a, b)
+    for _ in range(3):
+        assert np.array_equal(eng.gate_batch(key, "NAND", a, b), first)
+
+
 def test_gpu_keygen_is_a_valid_key_for_the_oracle(pkg, oracle, eng):
     """Keys made on the GPU (Keygen/keygen.c's role) must work in the CPU oracle and vice versa."""
     p = pkg.Params.default(20)
